@@ -1,0 +1,247 @@
+"""ctypes binding of libastrolink_b200.so (the C ABI in include/astrolink_b200.h)
+plus thin torch-tensor wrappers.  PyTorch only owns device memory and streams.
+
+There is no CPU fallback: if the library is missing or no CUDA device is
+present, every entry point raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libastrolink_b200.so")
+_lib = None
+
+AL_F32, AL_F64 = 0, 1
+LEAF = 32
+
+_c = ctypes
+_vp, _i64, _int, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_size_t
+
+_SIGS = {
+    "al_version": (_int, []),
+    "al_last_error": (_c.c_char_p, []),
+    "al_rescale_workspace_bytes": (_sz, [_i64, _int]),
+    "al_rescale": (_int, [_vp, _int, _i64, _int, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "al_index_bytes": (_sz, [_int, _i64, _int]),
+    "al_index_build_workspace_bytes": (_sz, [_int, _i64, _int]),
+    "al_index_build": (_int, [_vp, _int, _i64, _int, _vp, _sz, _vp, _sz, _vp]),
+    "al_index_positions": (_i64, [_i64]),
+    "al_index_perm": (_vp, [_vp]),
+    "al_knn_workspace_bytes": (_sz, [_int, _i64, _int, _int]),
+    "al_knn": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "al_logrho": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _vp, _vp]),
+    "al_normalise_workspace_bytes": (_sz, [_i64]),
+    "al_minmax": (_int, [_vp, _int, _i64, _vp, _vp, _sz, _vp]),
+    "al_normalise": (_int, [_vp, _int, _i64, _vp, _vp]),
+    "al_make_edges": (_int, [_vp, _int, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "al_sort_edges_workspace_bytes": (_sz, [_int, _i64]),
+    "al_sort_edges": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "al_aggregate_workspace_bytes": (_sz, [_int, _i64, _i64]),
+    "al_aggregate": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
+    "al_fp32_peak_tflops": (_int, [_vp, _vp]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NativeError(
+                f"{_LIB_PATH} is missing: build it with `python -m astrolink_b200.build` "
+                "(there is no CPU fallback)")
+        L = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().al_last_error().decode(errors="replace")
+        raise NativeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return AL_F32
+    if t.dtype == torch.float64:
+        return AL_F64
+    raise TypeError(f"float32/float64 expected, got {t.dtype}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise NativeError("astrolink_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+# --------------------------------------------------------------------------- stages
+def rescale(P):
+    """a1: P [n,d] cuda tensor -> (P_transform, std[d] float64)."""
+    L = lib()
+    n, d = P.shape
+    assert P.stride(1) == 1
+    out = torch.empty((n, d), dtype=P.dtype, device=P.device)
+    std = torch.empty(d, dtype=torch.float64, device=P.device)
+    ws = _ws(L.al_rescale_workspace_bytes(n, d), P.device)
+    _check(L.al_rescale(_ptr(P), _dt(P), n, d, P.stride(0), _ptr(out), _ptr(std), _ptr(ws), ws.numel(), _stream()), "al_rescale")
+    return out, std
+
+
+class Index:
+    """a2: spatial index over P_transform (replaces KDTree(P_transform))."""
+
+    def __init__(self, Pt):
+        L = lib()
+        assert Pt.is_contiguous()
+        self.n, self.d = Pt.shape
+        self.dtype = Pt.dtype
+        self.device = Pt.device
+        nbytes = L.al_index_bytes(_dt(Pt), self.n, self.d)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=Pt.device)
+        ws = _ws(L.al_index_build_workspace_bytes(_dt(Pt), self.n, self.d), Pt.device)
+        _check(L.al_index_build(_ptr(Pt), _dt(Pt), self.n, self.d, _ptr(self.buf), self.buf.numel(), _ptr(ws), ws.numel(),
+                                _stream()), "al_index_build")
+        self.positions = int(L.al_index_positions(self.n))
+
+    def perm(self):
+        """index position -> original point (uint32 viewed as int32 tensor; padding = -1)."""
+        return self.buf[256:256 + 4 * self.positions].view(torch.int32)
+
+    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False):
+        """a3: exact kNN of the points at index positions [pos_begin, pos_end)."""
+        L = lib()
+        pos_end = self.positions if pos_end is None else pos_end
+        rows = self.n if row_order == 0 else pos_end - pos_begin
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
+        pairs = torch.zeros(1, dtype=torch.int64, device=self.device) if count_pairs else None
+        ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)
+        _check(L.al_knn(_ptr(self.buf), pos_begin, pos_end, k, row_order, _ptr(idx), _ptr(d2), _ptr(pairs), _ptr(ws), ws.numel(),
+                        _stream()), "al_knn")
+        if count_pairs:
+            return d2, idx, pairs
+        return d2, idx
+
+
+def logrho(d2, idx, k_den, d_intrinsic, weights=None):
+    """a4/a5: raw log-density from squared kNN distances."""
+    L = lib()
+    nq, k = d2.shape
+    assert k == k_den and d2.is_contiguous()
+    out = torch.empty(nq, dtype=d2.dtype, device=d2.device)
+    if weights is not None:
+        assert weights.dtype == torch.float64 and idx is not None and idx.is_contiguous()
+    _check(L.al_logrho(_ptr(d2), _ptr(idx), _ptr(weights), _dt(d2), nq, k, int(d_intrinsic), _ptr(out), _stream()), "al_logrho")
+    return out
+
+
+def minmax(x):
+    L = lib()
+    mm = torch.empty(2, dtype=x.dtype, device=x.device)
+    ws = _ws(L.al_normalise_workspace_bytes(x.numel()), x.device)
+    _check(L.al_minmax(_ptr(x), _dt(x), x.numel(), _ptr(mm), _ptr(ws), ws.numel(), _stream()), "al_minmax")
+    return mm
+
+
+def normalise_(x, mm=None):
+    """a7: in-place min-max normalisation."""
+    L = lib()
+    if mm is None:
+        mm = minmax(x)
+    _check(L.al_normalise(_ptr(x), _dt(x), x.numel(), _ptr(mm), _stream()), "al_normalise")
+    return x
+
+
+def make_edges(logRho, kNN, k_link):
+    """a8: -> (weights [E], pairs [E,2] int32)."""
+    L = lib()
+    n = logRho.numel()
+    assert kNN.shape[0] == n and kNN.stride(1) == 1
+    E = n * (k_link - 1)
+    w = torch.empty(E, dtype=logRho.dtype, device=logRho.device)
+    pairs = torch.empty((E, 2), dtype=torch.int32, device=logRho.device)
+    _check(L.al_make_edges(_ptr(logRho), _dt(logRho), _ptr(kNN), kNN.stride(0), n, int(k_link), _ptr(w), _ptr(pairs), _stream()),
+           "al_make_edges")
+    return w, pairs
+
+
+def sort_edges(w, pairs, want_order=False):
+    """a9: canonical order (weight desc, slot asc) -> sorted pairs [E,2] (and slot order)."""
+    L = lib()
+    E = w.numel()
+    out = torch.empty_like(pairs)
+    order = torch.empty(E, dtype=torch.int32, device=w.device) if want_order else None
+    ws = _ws(L.al_sort_edges_workspace_bytes(_dt(w), E), w.device)
+    _check(L.al_sort_edges(_ptr(w), _dt(w), _ptr(pairs), E, _ptr(out), _ptr(order), _ptr(ws), ws.numel(), _stream()), "al_sort_edges")
+    return (out, order) if want_order else out
+
+
+def aggregate(logRho, sorted_pairs):
+    """a10/a11: -> (ordering [n] int32, groups [G,3] int32, prominences [G,2])."""
+    L = lib()
+    n = logRho.numel()
+    E = sorted_pairs.shape[0]
+    cap = n // 2 + 2
+    ordering = torch.empty(n, dtype=torch.int32, device=logRho.device)
+    groups = torch.empty((cap, 3), dtype=torch.int32, device=logRho.device)
+    prom = torch.empty((cap, 2), dtype=logRho.dtype, device=logRho.device)
+    G = ctypes.c_int64(0)
+    ws = _ws(L.al_aggregate_workspace_bytes(_dt(logRho), n, E), logRho.device)
+    _check(L.al_aggregate(_ptr(logRho), _dt(logRho), _ptr(sorted_pairs), n, E, _ptr(ordering), _ptr(groups), _ptr(prom),
+                          ctypes.byref(G), _ptr(ws), ws.numel(), _stream()), "al_aggregate")
+    g = int(G.value)
+    return ordering, groups[:g], prom[:g]
+
+
+def scatter_rows(src, perm, dst):
+    """dst[perm[p]] = src[p] for perm[p] >= 0."""
+    L = lib()
+    rows, cols = src.shape
+    assert src.element_size() == dst.element_size() and src.stride(1) == 1 and dst.stride(1) == 1
+    _check(L.al_scatter_rows(_ptr(src), _ptr(perm), rows, cols, src.stride(0), dst.stride(0), src.element_size(), _ptr(dst), _stream()),
+           "al_scatter_rows")
+    return dst
+
+
+def fp32_peak_tflops():
+    L = lib()
+    v = ctypes.c_double(0.0)
+    _check(L.al_fp32_peak_tflops(ctypes.byref(v), _stream()), "al_fp32_peak_tflops")
+    return float(v.value)
+
+
+def u32_numpy(t):
+    """int32 cuda tensor holding uint32 bit patterns -> numpy uint32."""
+    return t.detach().cpu().numpy().view(np.uint32)

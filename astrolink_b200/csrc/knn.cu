@@ -1,0 +1,60 @@
+// Host entry point of the kNN search (see knn_kernel.cuh for the kernel).
+#include "knn_kernel.cuh"
+
+#define DECL(T, D) int knn_launch_##T##_d##D(const KnnParams& p, cudaStream_t st);
+#define DECL_ALL(T) DECL(T, 1) DECL(T, 2) DECL(T, 3) DECL(T, 4) DECL(T, 5) DECL(T, 6) DECL(T, 7) DECL(T, 8)
+DECL_ALL(f32)
+DECL_ALL(f64)
+
+typedef int (*knn_fn)(const KnnParams&, cudaStream_t);
+static const knn_fn g_knn_f32[8] = {knn_launch_f32_d1, knn_launch_f32_d2, knn_launch_f32_d3, knn_launch_f32_d4,
+                                    knn_launch_f32_d5, knn_launch_f32_d6, knn_launch_f32_d7, knn_launch_f32_d8};
+static const knn_fn g_knn_f64[8] = {knn_launch_f64_d1, knn_launch_f64_d2, knn_launch_f64_d3, knn_launch_f64_d4,
+                                    knn_launch_f64_d5, knn_launch_f64_d6, knn_launch_f64_d7, knn_launch_f64_d8};
+
+extern "C" size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k) {
+    (void)dtype; (void)n; (void)d; (void)k;
+    return 256;
+}
+
+extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out,
+                      void* d2_out, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream) {
+    (void)ws; (void)ws_bytes;
+    IndexHeader h;
+    if (!index_lookup(index, &h)) {
+        AL_CUDA(cudaMemcpy(&h, index, sizeof(h), cudaMemcpyDeviceToHost));
+        AL_REQUIRE(h.magic == INDEX_MAGIC, AL_EINVAL, "al_knn: not an index built by al_index_build");
+        index_register(index, h);
+    }
+    AL_REQUIRE(k >= 1 && k <= h.n, AL_EINVAL, "al_knn: k must be in [1, n]");
+    AL_REQUIRE(k <= 128, AL_EINVAL, "al_knn: k > 128 is not supported");
+    AL_REQUIRE(h.d >= 1 && h.d <= 8, AL_EINVAL, "al_knn: d=%d not supported (1..8)", h.d);
+    i64 np = h.n_leaves * LEAF;
+    AL_REQUIRE(pos_begin >= 0 && pos_begin <= pos_end && pos_end <= np, AL_EINVAL, "al_knn: bad position range");
+    AL_REQUIRE(pos_begin % LEAF == 0 && pos_end % LEAF == 0, AL_EINVAL, "al_knn: positions must be multiples of %d", LEAF);
+    AL_REQUIRE(row_order == 0 || row_order == 1, AL_EINVAL, "al_knn: row_order must be 0 or 1");
+    KnnParams p;
+    const char* base = (const char*)index;
+    p.tiles = base + h.tiles_off;
+    for (int l = 0; l < MAX_WIDE_LEVELS; l++) { p.box[l] = base + h.box_off[l]; p.count[l] = h.count[l]; }
+    p.n_levels = h.n_levels;
+    p.tile_stride = h.tile_stride;
+    p.tile_hdr_bytes = h.tile_hdr_bytes;
+    p.tile_ids_off = h.tile_ids_off;
+    p.pair_block = h.pair_block;
+    p.leaf_begin = pos_begin / LEAF;
+    p.leaf_end = pos_end / LEAF;
+    p.n = h.n;
+    p.k = k;
+    p.row_order = row_order;
+    p.idx_out = idx_out;
+    p.d2_out = d2_out;
+    p.pairs = pairs_evaluated;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h.dtype == AL_F32) {
+        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride);
+        return g_knn_f32[h.d - 1](p, st);
+    }
+    p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride);
+    return g_knn_f64[h.d - 1](p, st);
+}

@@ -1,0 +1,421 @@
+// The streaming stages of the hot path around the kNN search:
+//   al_rescale      <- transform_data / _rescale_njit      (astrolink.py:218-243)
+//   al_logrho       <- _compute_logRho_njit / weighted      (astrolink.py:293-303, gather :283)
+//   al_minmax / al_normalise <- _normalise_njit             (astrolink.py:305-313)
+//   al_make_edges   <- _make_graph_njit                     (astrolink.py:355-382)
+//   al_sort_edges   <- pairs[edges.argsort()[::-1]]         (astrolink.py:341), canonical stable order
+// All are HBM-bound passes; see DESIGN.md for the algorithmic bytes of each.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void al_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* al_last_error(void) { return g_err; }
+extern "C" int al_version(void) { return 1; }
+
+constexpr int RS_MAXD = 16;
+constexpr int RS_BLOCKS = 592;   // 4 x 148 SMs
+constexpr int RS_THREADS = 256;
+
+// ---------------------------------------------------------------------------
+// a1 rescale: deterministic two-level column reductions in float64
+// ---------------------------------------------------------------------------
+template <typename T, bool CENTRED>
+__global__ void __launch_bounds__(RS_THREADS) column_sums_kernel(const T* __restrict__ P, i64 n, int d, i64 row_stride,
+                                                                 const double* __restrict__ mean, double* __restrict__ partial) {
+    double acc[RS_MAXD];
+#pragma unroll
+    for (int j = 0; j < RS_MAXD; j++) acc[j] = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const T* row = P + i * row_stride;
+#pragma unroll
+        for (int j = 0; j < RS_MAXD; j++)
+            if (j < d) {
+                double v = (double)row[j];
+                if (CENTRED) { v -= mean[j]; v *= v; }
+                acc[j] += v;
+            }
+    }
+    __shared__ double sm[RS_THREADS / 32][RS_MAXD];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < RS_MAXD; j++)
+        if (j < d) {
+            double v = acc[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) sm[w][j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < d) {
+        double v = 0.0;
+        for (int k = 0; k < RS_THREADS / 32; k++) v += sm[k][threadIdx.x];
+        partial[(i64)blockIdx.x * d + threadIdx.x] = v;
+    }
+}
+
+// one thread per column: fixed-order sum of the block partials
+template <bool FINAL_STD>
+__global__ void column_finish_kernel(const double* __restrict__ partial, int blocks, int d, i64 n, double* out) {
+    int j = threadIdx.x;
+    if (j >= d) return;
+    double v = 0.0;
+    for (int b = 0; b < blocks; b++) v += partial[(i64)b * d + j];
+    out[j] = FINAL_STD ? sqrt(v / (double)n) : v / (double)n;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rescale_apply_kernel(const T* __restrict__ P, i64 n, int d, i64 row_stride,
+                                                            const double* __restrict__ sd, T* __restrict__ out) {
+    i64 total = n * d;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        i64 i = t / d;
+        int j = (int)(t - i * d);
+        T v = P[i * row_stride + j];
+        double s = sd[j];
+        out[t] = s > 0.0 ? (T)(v / (T)s) : v;
+    }
+}
+
+extern "C" size_t al_rescale_workspace_bytes(int64_t n, int d) {
+    (void)n;
+    ArenaSizer s;
+    s.add<double>((size_t)RS_BLOCKS * d);
+    s.add<double>(d);
+    s.add<double>(d);
+    return s.off + 256;
+}
+
+template <typename T>
+static int rescale_impl(const T* P, i64 n, int d, i64 row_stride, T* out, double* std_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    double* partial = ar.get<double>((size_t)RS_BLOCKS * d);
+    double* mean = ar.get<double>(d);
+    double* sd = ar.get<double>(d);
+    AL_REQUIRE(ar.ok, AL_ENOMEM, "al_rescale: workspace too small");
+    int blocks = al_grid(n, RS_THREADS, RS_BLOCKS);
+    column_sums_kernel<T, false><<<blocks, RS_THREADS, 0, st>>>(P, n, d, row_stride, nullptr, partial);
+    AL_CHECK_LAUNCH();
+    column_finish_kernel<false><<<1, 32, 0, st>>>(partial, blocks, d, n, mean);
+    AL_CHECK_LAUNCH();
+    column_sums_kernel<T, true><<<blocks, RS_THREADS, 0, st>>>(P, n, d, row_stride, mean, partial);
+    AL_CHECK_LAUNCH();
+    column_finish_kernel<true><<<1, 32, 0, st>>>(partial, blocks, d, n, sd);
+    AL_CHECK_LAUNCH();
+    rescale_apply_kernel<T><<<al_grid(n * d, 256), 256, 0, st>>>(P, n, d, row_stride, sd, out);
+    AL_CHECK_LAUNCH();
+    if (std_out) AL_CUDA(cudaMemcpyAsync(std_out, sd, sizeof(double) * d, cudaMemcpyDeviceToDevice, st));
+    return AL_OK;
+}
+
+extern "C" int al_rescale(const void* P, int dtype, int64_t n, int d, int64_t row_stride, void* Pt_out, double* std_out,
+                          void* ws, size_t ws_bytes, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_rescale: bad dtype");
+    AL_REQUIRE(n >= 1 && d >= 1 && d <= RS_MAXD && row_stride >= d, AL_EINVAL, "al_rescale: bad shape (d must be <= %d)", RS_MAXD);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AL_F32) return rescale_impl<float>((const float*)P, n, d, row_stride, (float*)Pt_out, std_out, ws, ws_bytes, st);
+    return rescale_impl<double>((const double*)P, n, d, row_stride, (double*)Pt_out, std_out, ws, ws_bytes, st);
+}
+
+// ---------------------------------------------------------------------------
+// a4/a5 density: one thread per query row
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, const u32* __restrict__ idx,
+                                                     const double* __restrict__ weights, i64 nq, int k, double half_d,
+                                                     T* __restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const T* r = d2 + i * k;
+    const T coreT = r[k - 1];
+    const double core = (double)coreT;
+    double v;
+    if (weights == nullptr) {
+        T s = (T)0;
+        for (int j = 0; j < k; j++) s += r[j];
+        v = ((double)k - (double)(T)(s / coreT)) / pow(core, half_d);
+    } else {
+        const u32* ir = idx + i * k;
+        double sw = 0.0, swd = 0.0;
+        for (int j = 0; j < k; j++) {
+            double w = weights[ir[j]];
+            sw += w;
+            swd += w * (double)r[j];
+        }
+        v = (sw - swd / core) / pow(core, half_d);
+    }
+    out[i] = (T)log(v);
+}
+
+extern "C" int al_logrho(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k,
+                         int d_intrinsic, void* logrho_out, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_logrho: bad dtype");
+    AL_REQUIRE(nq >= 0 && k >= 1 && d_intrinsic >= 1, AL_EINVAL, "al_logrho: bad shape");
+    AL_REQUIRE(weights == nullptr || idx != nullptr, AL_EINVAL, "al_logrho: weights need idx");
+    if (nq == 0) return AL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((nq + 255) / 256);
+    if (dtype == AL_F32)
+        logrho_kernel<float><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, (float*)logrho_out);
+    else
+        logrho_kernel<double><<<grid, 256, 0, st>>>((const double*)d2, idx, weights, nq, k, d_intrinsic / 2.0, (double*)logrho_out);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// a7 min/max + normalise
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const T* __restrict__ x, i64 n, T* __restrict__ partial) {
+    T mn = (T)INFINITY, mx = -(T)INFINITY;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        T v = x[i];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    __shared__ T smn[8], smx[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { mn = smn[w] < mn ? smn[w] : mn; mx = smx[w] > mx ? smx[w] : mx; }
+        partial[2 * blockIdx.x] = mn;
+        partial[2 * blockIdx.x + 1] = mx;
+    }
+}
+template <typename T>
+__global__ void minmax_final_kernel(const T* __restrict__ partial, int blocks, T* out) {
+    T mn = (T)INFINITY, mx = -(T)INFINITY;
+    for (int b = threadIdx.x; b < blocks; b += 32) {
+        T a = partial[2 * b], c = partial[2 * b + 1];
+        mn = a < mn ? a : mn;
+        mx = c > mx ? c : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (threadIdx.x == 0) { out[0] = mn; out[1] = mx; }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) normalise_kernel(T* x, i64 n, const T* __restrict__ mm) {
+    const T mn = mm[0], range = mm[1] - mm[0];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) x[i] = (x[i] - mn) / range;
+}
+
+extern "C" size_t al_normalise_workspace_bytes(int64_t n) {
+    (void)n;
+    return al_align((size_t)RS_BLOCKS * 2 * 8) + al_align(16) + 256;
+}
+
+extern "C" int al_minmax(const void* x, int dtype, int64_t n, void* minmax_out, void* ws, size_t ws_bytes, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_minmax: bad dtype");
+    AL_REQUIRE(n >= 1 && minmax_out != nullptr, AL_EINVAL, "al_minmax: bad arguments");
+    Arena ar(ws, ws_bytes);
+    double* partial = ar.get<double>((size_t)RS_BLOCKS * 2);
+    AL_REQUIRE(ar.ok, AL_ENOMEM, "al_minmax: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = al_grid(n, 256, RS_BLOCKS);
+    if (dtype == AL_F32) {
+        minmax_partial_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, n, (float*)partial);
+        minmax_final_kernel<float><<<1, 32, 0, st>>>((const float*)partial, blocks, (float*)minmax_out);
+    } else {
+        minmax_partial_kernel<double><<<blocks, 256, 0, st>>>((const double*)x, n, partial);
+        minmax_final_kernel<double><<<1, 32, 0, st>>>(partial, blocks, (double*)minmax_out);
+    }
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+extern "C" int al_normalise(void* x, int dtype, int64_t n, const void* minmax, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_normalise: bad dtype");
+    AL_REQUIRE(n >= 1 && minmax != nullptr, AL_EINVAL, "al_normalise: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AL_F32) normalise_kernel<float><<<al_grid(n, 256), 256, 0, st>>>((float*)x, n, (const float*)minmax);
+    else normalise_kernel<double><<<al_grid(n, 256), 256, 0, st>>>((double*)x, n, (const double*)minmax);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// a8 edges: one thread per point, L-1 edge slots each
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) make_edges_kernel(const T* __restrict__ logrho, const u32* __restrict__ knn, i64 knn_stride,
+                                                         i64 n, int L, T* __restrict__ w_out, uint2* __restrict__ pairs_out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T li = logrho[i];
+    i64 pos = i * (L - 1);
+    const i64 end = pos + (L - 1);
+    const u32* row = knn + i * knn_stride;
+    for (int r = 0; r < L && pos < end; r++) {
+        const u32 j = row[r];
+        if ((i64)j == i) continue;
+        const T lj = logrho[j];
+        if (li >= lj) { w_out[pos] = lj; pairs_out[pos] = make_uint2((u32)i, j); }
+        else { w_out[pos] = li; pairs_out[pos] = make_uint2(j, (u32)i); }
+        pos++;
+    }
+}
+
+extern "C" int al_make_edges(const void* logrho, int dtype, const uint32_t* knn, int64_t knn_stride, int64_t n, int L,
+                             void* weights_out, uint32_t* pairs_out, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_make_edges: bad dtype");
+    AL_REQUIRE(n >= 1 && L >= 2 && knn_stride >= L, AL_EINVAL, "al_make_edges: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == AL_F32)
+        make_edges_kernel<float><<<grid, 256, 0, st>>>((const float*)logrho, knn, knn_stride, n, L, (float*)weights_out, (uint2*)pairs_out);
+    else
+        make_edges_kernel<double><<<grid, 256, 0, st>>>((const double*)logrho, knn, knn_stride, n, L, (double*)weights_out, (uint2*)pairs_out);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// a9 canonical edge order: stable descending radix sort of (weight, slot)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iota_kernel(u32* v, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) v[i] = (u32)i;
+}
+__global__ void __launch_bounds__(256) gather_pairs_kernel(const uint2* __restrict__ pairs, const u32* __restrict__ order, i64 E,
+                                                           uint2* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (i64)gridDim.x * blockDim.x) out[i] = pairs[order[i]];
+}
+
+template <typename T>
+static size_t sort_tmp_bytes(i64 E) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (const T*)nullptr, (T*)nullptr, (const u32*)nullptr, (u32*)nullptr, E, 0,
+                                              (int)sizeof(T) * 8, (cudaStream_t)0);
+    return b;
+}
+
+extern "C" size_t al_sort_edges_workspace_bytes(int dtype, int64_t E) {
+    ArenaSizer s;
+    s.add<char>((size_t)E * (dtype == AL_F64 ? 8 : 4));
+    s.add<u32>(E);
+    s.add<u32>(E);
+    s.add<char>(dtype == AL_F64 ? sort_tmp_bytes<double>(E) : sort_tmp_bytes<float>(E));
+    return s.off + 256;
+}
+
+template <typename T>
+static int sort_edges_impl(const T* w, const uint2* pairs, i64 E, uint2* out, u32* order_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    T* keys_out = (T*)ar.get<char>((size_t)E * sizeof(T));
+    u32* vals_in = ar.get<u32>(E);
+    u32* vals_out = ar.get<u32>(E);
+    size_t tb = sort_tmp_bytes<T>(E);
+    void* tmp = ar.get<char>(tb);
+    AL_REQUIRE(ar.ok, AL_ENOMEM, "al_sort_edges: workspace too small");
+    iota_kernel<<<al_grid(E, 256), 256, 0, st>>>(vals_in, E);
+    AL_CHECK_LAUNCH();
+    u32* dst = order_out ? order_out : vals_out;
+    AL_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, w, keys_out, vals_in, dst, E, 0, (int)sizeof(T) * 8, st));
+    gather_pairs_kernel<<<al_grid(E, 256), 256, 0, st>>>(pairs, dst, E, out);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+extern "C" int al_sort_edges(const void* weights, int dtype, const uint32_t* pairs, int64_t E, uint32_t* sorted_pairs_out,
+                             uint32_t* order_out, void* ws, size_t ws_bytes, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_sort_edges: bad dtype");
+    AL_REQUIRE(E >= 1 && E < 0xffffffffll, AL_EINVAL, "al_sort_edges: E out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AL_F32)
+        return sort_edges_impl<float>((const float*)weights, (const uint2*)pairs, E, (uint2*)sorted_pairs_out, order_out, ws, ws_bytes, st);
+    return sort_edges_impl<double>((const double*)weights, (const uint2*)pairs, E, (uint2*)sorted_pairs_out, order_out, ws, ws_bytes, st);
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const V* __restrict__ src, const u32* __restrict__ perm, i64 rows, int cols,
+                                                           int src_stride, int dst_stride, V* __restrict__ dst) {
+    i64 total = rows * cols;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        i64 r = t / cols;
+        int c = (int)(t - r * cols);
+        u32 to = perm[r];
+        if (to != 0xffffffffu) dst[(i64)to * dst_stride + c] = src[r * src_stride + c];
+    }
+}
+
+extern "C" int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int cols, int src_stride, int dst_stride,
+                               int elem_bytes, void* dst, void* stream) {
+    AL_REQUIRE(elem_bytes == 4 || elem_bytes == 8, AL_EINVAL, "al_scatter_rows: elem_bytes must be 4 or 8");
+    if (rows <= 0) return AL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (elem_bytes == 4)
+        scatter_rows_kernel<u32><<<al_grid(rows * cols, 256), 256, 0, st>>>((const u32*)src, perm, rows, cols, src_stride, dst_stride, (u32*)dst);
+    else
+        scatter_rows_kernel<u64><<<al_grid(rows * cols, 256), 256, 0, st>>>((const u64*)src, perm, rows, cols, src_stride, dst_stride, (u64*)dst);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
+// FP32 FMA issue-rate probe (roofline denominator of the kNN kernel)
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, float a, float b, int iters) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+extern "C" int al_fp32_peak_tflops(double* tflops_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    AL_CUDA(cudaGetDevice(&dev));
+    AL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* out = nullptr;
+    AL_CUDA(cudaMalloc(&out, 4));   // probe only; not on the hot path
+    cudaEvent_t e0, e1;
+    AL_CUDA(cudaEventCreate(&e0));
+    AL_CUDA(cudaEventCreate(&e1));
+    const int iters = 8192, blocks = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        AL_CUDA(cudaEventRecord(e0, st));
+        fp32_probe_kernel<<<blocks, 256, 0, st>>>(out, 1.0001f, 0.5f, iters);
+        AL_CUDA(cudaEventRecord(e1, st));
+        AL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        AL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = (double)blocks * 256 * iters * 8 * 2 / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_host = best;
+    return AL_OK;
+}

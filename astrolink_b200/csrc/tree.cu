@@ -1,0 +1,340 @@
+// Spatial index build: replaces pykdtree's KDTree(P_transform)
+// (reference astrolink/astrolink.py:270).
+//
+// A balanced axis-aligned split tree is built level-synchronously: every round
+// sorts all points by (node, coordinate along the node's widest dimension) with
+// one CUB radix sort, then every node of more than one leaf is cut at the
+// multiple of the largest power of two inside its leaf range.  That rule makes
+// every aligned block of 32^h leaves a subtree, so the 32-ary box hierarchy the
+// search walks has tight boxes.  The tree only decides the ORDER of the points;
+// the search result does not depend on it (boxes are exact bounds).
+#include <cub/cub.cuh>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "index.cuh"
+
+constexpr int MAXD = 16;
+
+// ---------------------------------------------------------------------------
+// header registry
+// ---------------------------------------------------------------------------
+static std::mutex g_reg_mu;
+static std::unordered_map<const void*, IndexHeader> g_reg;
+
+bool index_lookup(const void* index, IndexHeader* out) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_reg.find(index);
+    if (it == g_reg.end()) return false;
+    *out = it->second;
+    return true;
+}
+void index_register(const void* index, const IndexHeader& h) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_reg[index] = h;
+}
+
+// ---------------------------------------------------------------------------
+__host__ __device__ static inline u32 split_mid(u32 a, u32 b) {
+    u32 x = a ^ (b - 1);
+#ifdef __CUDA_ARCH__
+    int h = 31 - __clz(x);
+#else
+    int h = 31 - __builtin_clz(x);
+#endif
+    return ((b - 1) >> h) << h;
+}
+
+static int tree_depth(i64 n_leaves) {
+    if (n_leaves <= 1) return 0;
+    int p = 63 - __builtin_clzll((unsigned long long)(n_leaves - 1));
+    int r = tree_depth(n_leaves - ((i64)1 << p));
+    return 1 + (p > r ? p : r);
+}
+
+__global__ void tree_init_kernel(u32* perm, u32* nodeA, u32* nodeB, i64 n, i64 n_leaves) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 p = i; p < n; p += stride) perm[p] = (u32)p;
+    for (i64 l = i; l < n_leaves; l += stride) { nodeA[l] = 0; nodeB[l] = (u32)n_leaves; }
+}
+
+constexpr int BOUNDS_CHUNK = 16;   // leaves per warp
+
+template <typename T>
+__global__ void __launch_bounds__(256) tree_node_bounds_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
+                                                               const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
+                                                               u32* bbox_lo, u32* bbox_hi, i64 n, i64 n_leaves, int d) {
+    int lane = threadIdx.x & 31;
+    i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    i64 leaf0 = warp * BOUNDS_CHUNK;
+    if (leaf0 >= n_leaves) return;
+    float mn[MAXD], mx[MAXD];
+    i64 cur = -1;
+    auto flush = [&]() {
+        if (cur < 0) return;
+#pragma unroll
+        for (int j = 0; j < MAXD; j++) {
+            if (j < d) {
+                float a = mn[j], b = mx[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                }
+                if (lane == 0) {
+                    atomicMin(&bbox_lo[cur * d + j], f32_to_ordered(a));
+                    atomicMax(&bbox_hi[cur * d + j], f32_to_ordered(b));
+                }
+            }
+        }
+    };
+    for (int c = 0; c < BOUNDS_CHUNK; c++) {
+        i64 leaf = leaf0 + c;
+        if (leaf >= n_leaves) break;
+        u32 a = nodeA[leaf];
+        if (nodeB[leaf] - a <= 1) continue;
+        if ((i64)a != cur) {
+            flush();
+            cur = a;
+#pragma unroll
+            for (int j = 0; j < MAXD; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+        }
+        i64 p = leaf * LEAF + lane;
+        if (p < n) {
+            const T* row = P + (i64)perm[p] * d;
+#pragma unroll
+            for (int j = 0; j < MAXD; j++)
+                if (j < d) {
+                    float v = (float)row[j];
+                    mn[j] = fminf(mn[j], v);
+                    mx[j] = fmaxf(mx[j], v);
+                }
+        }
+    }
+    flush();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
+                                                             const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
+                                                             const u32* __restrict__ bbox_lo, const u32* __restrict__ bbox_hi,
+                                                             u64* keys, i64 n, int d) {
+    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    i64 leaf = p / LEAF;
+    u32 a = nodeA[leaf];
+    u32 low;
+    if (nodeB[leaf] - a > 1) {
+        int dim = 0;
+        u32 best = 0;
+        for (int j = 0; j < d; j++) {
+            // ordered-uint difference is monotone in the float extent for finite values of equal sign
+            // pattern; use the float extent itself for a faithful argmax
+            u32 lo = bbox_lo[(i64)a * d + j], hi = bbox_hi[(i64)a * d + j];
+            auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
+            float ext = dec(hi) - dec(lo);
+            u32 e = __float_as_uint(ext > 0.f ? ext : 0.f);
+            if (j == 0 || e > best) { best = e; dim = j; }
+        }
+        low = f32_to_ordered((float)P[(i64)perm[p] * d + dim]);
+    } else {
+        low = (u32)(p - leaf * LEAF);
+    }
+    keys[p] = ((u64)a << 32) | low;
+}
+
+__global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves) {
+    i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_leaves) return;
+    u32 a = nodeA[l], b = nodeB[l];
+    if (b - a > 1) {
+        u32 mid = split_mid(a, b);
+        if ((u32)l < mid) nodeB[l] = mid; else nodeA[l] = mid;
+    }
+}
+
+// one warp per leaf: gather the leaf's points into its tile
+template <typename T>
+__global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restrict__ P, u32* perm, char* tiles,
+                                                               T* box_lo, T* box_hi, IndexHeader h) {
+    int lane = threadIdx.x & 31;
+    i64 leaf = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (leaf >= h.n_leaves) return;
+    const int d = h.d;
+    i64 p = leaf * LEAF + lane;
+    bool valid = p < h.n;
+    u32 id = valid ? perm[p] : 0xffffffffu;
+    if (!valid) perm[p] = 0xffffffffu;
+    char* tile = tiles + leaf * (i64)h.tile_stride;
+    T* hdr = (T*)tile;
+    T* coords = (T*)(tile + h.tile_hdr_bytes);
+    u32* ids = (u32*)(tile + h.tile_ids_off);
+    ids[lane] = id;
+    const T inf = (T)INFINITY;
+    int pb = lane >> 1, half = lane & 1;
+    for (int j = 0; j < d; j++) {
+        T v = valid ? P[(i64)id * d + j] : inf;
+        coords[pb * h.pair_block + 2 * j + half] = v;
+        T a = valid ? v : inf, b = valid ? v : -inf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, b, o);
+            a = a2 < a ? a2 : a;
+            b = b2 > b ? b2 : b;
+        }
+        if (lane == 0) {
+            hdr[j] = a;
+            hdr[d + j] = b;
+            box_lo[(i64)j * h.n_leaves + leaf] = a;
+            box_hi[(i64)j * h.n_leaves + leaf] = b;
+        }
+    }
+    // zero the padding elements of the pair block so the tile is fully defined
+    for (int e = 2 * d + half; e < h.pair_block; e += 2) coords[pb * h.pair_block + e] = (T)0;
+}
+
+template <typename T>
+__global__ void tree_build_level_kernel(const T* __restrict__ clo, const T* __restrict__ chi, i64 n_child,
+                                        T* plo, T* phi, i64 n_parent, int d) {
+    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_parent * d) return;
+    i64 node = t % n_parent;
+    int j = (int)(t / n_parent);
+    i64 c0 = node * FANOUT, c1 = c0 + FANOUT < n_child ? c0 + FANOUT : n_child;
+    T a = (T)INFINITY, b = -(T)INFINITY;
+    for (i64 c = c0; c < c1; c++) {
+        T x = clo[(i64)j * n_child + c], y = chi[(i64)j * n_child + c];
+        a = x < a ? x : a;
+        b = y > b ? y : b;
+    }
+    plo[(i64)j * n_parent + node] = a;
+    phi[(i64)j * n_parent + node] = b;
+}
+
+// ---------------------------------------------------------------------------
+struct BuildWs {
+    u64 *keys0, *keys1;
+    u32 *vals1;
+    u32 *nodeA, *nodeB;
+    u32 *bbox_lo, *bbox_hi;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+
+static size_t sort_temp_bytes(i64 n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const u64*)nullptr, (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr,
+                                    (i64)n, 0, 64, (cudaStream_t)0);
+    return bytes;
+}
+
+extern "C" size_t al_index_bytes(int dtype, int64_t n, int d) {
+    IndexHeader h;
+    index_layout(dtype, n, d, &h);
+    return h.total_bytes;
+}
+
+extern "C" int64_t al_index_positions(int64_t n) { return (n + LEAF - 1) / LEAF * LEAF; }
+
+extern "C" const uint32_t* al_index_perm(const void* index) { return (const uint32_t*)((const char*)index + 256); }
+
+extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
+    (void)dtype;
+    i64 n_leaves = (n + LEAF - 1) / LEAF;
+    ArenaSizer s;
+    s.add<u64>(n);
+    s.add<u64>(n);
+    s.add<u32>(n);
+    s.add<u32>(n_leaves);
+    s.add<u32>(n_leaves);
+    s.add<u32>(n_leaves * d);
+    s.add<u32>(n_leaves * d);
+    s.add<char>(sort_temp_bytes(n));
+    return s.off + 256;
+}
+
+template <typename T>
+static int index_build_impl(const T* P, const IndexHeader& h, void* index, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const i64 n = h.n, n_leaves = h.n_leaves;
+    const int d = h.d;
+    Arena ar(ws, ws_bytes);
+    BuildWs w;
+    w.keys0 = ar.get<u64>(n);
+    w.keys1 = ar.get<u64>(n);
+    w.vals1 = ar.get<u32>(n);
+    w.nodeA = ar.get<u32>(n_leaves);
+    w.nodeB = ar.get<u32>(n_leaves);
+    w.bbox_lo = ar.get<u32>(n_leaves * d);
+    w.bbox_hi = ar.get<u32>(n_leaves * d);
+    w.cub_bytes = sort_temp_bytes(n);
+    w.cub_tmp = ar.get<char>(w.cub_bytes);
+    AL_REQUIRE(ar.ok, AL_ENOMEM, "al_index_build: workspace too small (%zu bytes given)", ws_bytes);
+
+    char* base = (char*)index;
+    u32* perm = (u32*)(base + h.perm_off);
+    u32* vals[2] = {perm, w.vals1};
+    u64* keys[2] = {w.keys0, w.keys1};
+    int cur = 0;
+
+    tree_init_kernel<<<al_grid(n, 256), 256, 0, st>>>(perm, w.nodeA, w.nodeB, n, n_leaves);
+    AL_CHECK_LAUNCH();
+
+    int rounds = tree_depth(n_leaves);
+    int node_bits = 1;
+    while (((i64)1 << node_bits) < n_leaves) node_bits++;
+    for (int r = 0; r < rounds; r++) {
+        AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
+        AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
+        i64 n_warps = (n_leaves + BOUNDS_CHUNK - 1) / BOUNDS_CHUNK;
+        tree_node_bounds_kernel<T><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, st>>>(
+            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, n, n_leaves, d);
+        AL_CHECK_LAUNCH();
+        tree_make_keys_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, keys[cur], n, d);
+        AL_CHECK_LAUNCH();
+        size_t tb = w.cub_bytes;
+        AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
+                                                32 + node_bits, st));
+        cur ^= 1;
+        tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves);
+        AL_CHECK_LAUNCH();
+    }
+    if (vals[cur] != perm) AL_CUDA(cudaMemcpyAsync(perm, vals[cur], sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+
+    const int eb = (int)sizeof(T);
+    T* lo0 = (T*)(base + h.box_off[0]);
+    T* hi0 = lo0 + (i64)d * h.count[0];
+    tree_build_tiles_kernel<T><<<(unsigned)((n_leaves * 32 + 255) / 256), 256, 0, st>>>(P, perm, base + h.tiles_off, lo0, hi0, h);
+    AL_CHECK_LAUNCH();
+    for (int l = 1; l <= h.n_levels; l++) {
+        T* clo = (T*)(base + h.box_off[l - 1]);
+        T* chi = clo + (i64)d * h.count[l - 1];
+        T* plo = (T*)(base + h.box_off[l]);
+        T* phi = plo + (i64)d * h.count[l];
+        i64 work = h.count[l] * d;
+        tree_build_level_kernel<T><<<(unsigned)((work + 127) / 128), 128, 0, st>>>(clo, chi, h.count[l - 1], plo, phi, h.count[l], d);
+        AL_CHECK_LAUNCH();
+    }
+    (void)eb;
+    AL_CUDA(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    index_register(index, h);
+    return AL_OK;
+}
+
+extern "C" int al_index_build(const void* Pt, int dtype, int64_t n, int d, void* index, size_t index_bytes, void* ws,
+                              size_t ws_bytes, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_index_build: dtype must be AL_F32 or AL_F64");
+    AL_REQUIRE(n >= 1 && n < 0xffffffffll, AL_EINVAL, "al_index_build: n out of range");
+    AL_REQUIRE(d >= 1 && d <= MAXD, AL_EINVAL, "al_index_build: d must be in [1, %d]", MAXD);
+    static_assert(sizeof(IndexHeader) <= 256, "IndexHeader must fit its slot");
+    IndexHeader h;
+    index_layout(dtype, n, d, &h);
+    AL_REQUIRE(index_bytes >= h.total_bytes, AL_ENOMEM, "al_index_build: index buffer too small");
+    AL_REQUIRE(((uintptr_t)index & 255) == 0, AL_EINVAL, "al_index_build: index must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == AL_F32) return index_build_impl<float>((const float*)Pt, h, index, ws, ws_bytes, st);
+    return index_build_impl<double>((const double*)Pt, h, index, ws, ws_bytes, st);
+}

@@ -1,0 +1,143 @@
+/*
+ * astrolink_b200.h -- C ABI of the B200-native AstroLink hot path.
+ *
+ * The reference (william-h-oliver/astrolink) has no FFI layer of its own: its
+ * hot path is Python methods calling numba kernels and pykdtree.  Each entry
+ * point below replaces one of those calls; the citation is the reference
+ * file:line a maintainer would redirect (see INTEGRATION.md for the ctypes
+ * binding).  All citations are into astrolink/astrolink.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - every data pointer is a DEVICE pointer owned by the caller, unless its
+ *     name ends in _host.  Functions never allocate device memory: scratch is
+ *     passed in as (ws, ws_bytes), sized by the matching *_workspace_bytes().
+ *   - `dtype` selects the floating type of the data: AL_F32 or AL_F64 (the
+ *     dtype of P in the reference; float64 input is computed in float64).
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - functions are asynchronous on `stream` unless stated otherwise.
+ *   - return 0 on success, a negative AL_E* code otherwise; al_last_error()
+ *     returns a message for the calling thread's last failure.
+ *   - indices are uint32 (n < 2^32-1, as the reference's reachable dispatch,
+ *     astrolink.py:268,345-350).
+ */
+#ifndef ASTROLINK_B200_H
+#define ASTROLINK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AL_F32 0
+#define AL_F64 1
+
+#define AL_OK 0
+#define AL_EINVAL (-1)    /* bad argument */
+#define AL_ENOMEM (-2)    /* workspace / index buffer too small */
+#define AL_ECUDA (-3)     /* CUDA runtime error, see al_last_error() */
+#define AL_EINTERNAL (-4) /* internal consistency check failed */
+
+int al_version(void);
+const char* al_last_error(void);
+
+/* ---- a1: transform_data / _rescale_njit (astrolink.py:218-243) ----------
+ * Pt[i][j] = P[i][j] / std_j (population std, accumulated in float64).  A
+ * zero-variance column is copied through.  P is row-major [n][d] with a row
+ * stride of `row_stride` elements.  std_out (device, d doubles) may be NULL. */
+size_t al_rescale_workspace_bytes(int64_t n, int d);
+int al_rescale(const void* P, int dtype, int64_t n, int d, int64_t row_stride, void* Pt_out,
+               double* std_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a2: KDTree(P_transform) (astrolink.py:270) -------------------------
+ * Builds the spatial index used by al_knn: a balanced median-split tree held
+ * as a permutation of the points into 32-point leaf tiles plus bounding boxes.
+ * `index` is an opaque device buffer of al_index_bytes(); Pt is row-major
+ * [n][d] contiguous and is not referenced after the call returns (the index
+ * holds its own tiled copy).  Synchronous (it sizes its passes on the host). */
+size_t al_index_bytes(int dtype, int64_t n, int d);
+size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d);
+int al_index_build(const void* Pt, int dtype, int64_t n, int d, void* index, size_t index_bytes,
+                   void* ws, size_t ws_bytes, void* stream);
+/* number of index positions (n rounded up to whole leaves) and the position ->
+ * original-index permutation (device, uint32[al_index_positions], padding = 0xffffffff) */
+int64_t al_index_positions(int64_t n);
+const uint32_t* al_index_perm(const void* index);
+
+/* ---- a3: KDTree.query(P_t, k=k_den, sqr_dists=True) (astrolink.py:279) ---
+ * Exact k nearest neighbours (self included) of the points at index positions
+ * [pos_begin, pos_end) (multiples of 32, or the end) against all n points.
+ * Distance: acc = fma(q_j - p_j, q_j - p_j, acc), j = 0..d-1, in `dtype`.
+ * Order: (distance, original index) ascending -- ties broken by index.
+ * row_order 0: row of original point i written at row i of idx_out/d2_out
+ *              ([n][k] arrays);
+ * row_order 1: row of index position p written at row p - pos_begin
+ *              ([pos_end - pos_begin][k] arrays; padding rows are filled with
+ *              0xffffffff / +inf).
+ * pairs_evaluated (device uint64, may be NULL) is incremented by the number of
+ * (query, candidate) distance evaluations, for roofline accounting. */
+size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k);
+int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order,
+           uint32_t* idx_out, void* d2_out, unsigned long long* pairs_evaluated,
+           void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a4/a5: _compute_logRho_njit / _compute_weighted_logRho_njit
+ *      (astrolink.py:293-303, gather of weights[indices] at :283) ----------
+ * out[i] = log((sum_j w_j - sum_j w_j d2[i][j] / d2[i][k-1]) / d2[i][k-1]^(d_intrinsic/2)),
+ * w_j = weights[idx[i][j]] (double) or 1 when weights == NULL.  Evaluated in
+ * float64, stored in `dtype` (as the reference's store at :282). */
+int al_logrho(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq,
+              int k, int d_intrinsic, void* logrho_out, void* stream);
+
+/* ---- a7: _normalise_njit (astrolink.py:305-313) -------------------------
+ * x <- (x - min) / (max - min) over all n.  minmax_out (device, 2 values of
+ * `dtype`, may be NULL) receives {min, max}. */
+size_t al_normalise_workspace_bytes(int64_t n);
+int al_minmax(const void* x, int dtype, int64_t n, void* minmax_out, void* ws, size_t ws_bytes, void* stream);
+int al_normalise(void* x, int dtype, int64_t n, const void* minmax, void* stream);
+
+/* ---- a8: _make_graph_njit (astrolink.py:355-382) ------------------------
+ * knn is [n][knn_stride] uint32, the first L columns are used.  Row i owns
+ * edge slots [i(L-1), (i+1)(L-1)): the entry equal to i is skipped (if absent
+ * the last entry is dropped); pair = (denser, sparser), ties -> (i, j);
+ * weight = logrho of the sparser end.  weights_out: `dtype`[E];
+ * pairs_out: uint32[E][2]. */
+int al_make_edges(const void* logrho, int dtype, const uint32_t* knn, int64_t knn_stride, int64_t n,
+                  int L, void* weights_out, uint32_t* pairs_out, void* stream);
+
+/* ---- a9: pairs[edges.argsort()[::-1]] (astrolink.py:341) ----------------
+ * Canonical total order: weight descending, slot ascending (the reference's
+ * argsort is unstable).  Stable descending radix sort (CUB).
+ * order_out (uint32[E], may be NULL) receives the sorted slot indices. */
+size_t al_sort_edges_workspace_bytes(int dtype, int64_t E);
+int al_sort_edges(const void* weights, int dtype, const uint32_t* pairs, int64_t E,
+                  uint32_t* sorted_pairs_out, uint32_t* order_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a10/a11: _aggregate_njit_float{32,64}_uint32 (astrolink.py:384-604)
+ * sorted_pairs: uint32[E][2] in the order above.  The float32 variant applies
+ * the final noise correction to prominence column 0 (:484), the float64
+ * variant to column 1 (:595); the variant follows `dtype` as the reference's
+ * dispatch does (:345-350).
+ * Outputs: ordering uint32[n]; groups uint32[G][3] = [geq_start, leq_start,
+ * leq_end]; prominences `dtype`[G][2]; capacity n/2 rows each.
+ * *n_groups_host (HOST pointer) receives G.  Synchronous. */
+size_t al_aggregate_workspace_bytes(int dtype, int64_t n, int64_t E);
+int al_aggregate(const void* logrho, int dtype, const uint32_t* sorted_pairs, int64_t n, int64_t E,
+                 uint32_t* ordering_out, uint32_t* groups_out, void* prominences_out,
+                 int64_t* n_groups_host, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- helpers ------------------------------------------------------------ */
+/* scatter rows: dst[perm[p]][0..cols) = src[p][0..cols) for p in [0, rows), skipping
+ * perm == 0xffffffff; elem_bytes is 4 or 8. */
+int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int cols, int src_stride,
+                    int dst_stride, int elem_bytes, void* dst, void* stream);
+/* measured FP32 FMA issue rate of this GPU in TFLOP/s (2 flop per FMA); used as
+ * the roofline denominator of the kNN kernel.  Synchronous. */
+int al_fp32_peak_tflops(double* tflops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,114 @@
+"""GPU parity of each stage of the hot path, called through the C ABI, against
+the committed golden vectors (reference outputs) and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+def _native():
+    from astrolink_b200 import _native
+    _native.require_cuda()
+    return _native
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_knn_bit_exact_vs_golden(name, golden):
+    nat = _native()
+    g = golden(name)
+    Pt = _cu(g["P_transform"])
+    k = int(g["k_den"])
+    index = nat.Index(Pt)
+    d2, idx = index.knn(k)
+    torch.cuda.synchronize()
+    assert (nat.u32_numpy(idx) == g["knn_idx"]).all(), "kNN indices must be bit-exact (ties by index)"
+    assert (d2.cpu().numpy() == g["knn_d2"]).all(), "squared distances must be bit-exact (same fma chain)"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_knn_tree_order_rows(name, golden):
+    nat = _native()
+    g = golden(name)
+    Pt = _cu(g["P_transform"])
+    k = int(g["k_den"])
+    index = nat.Index(Pt)
+    d2, idx = index.knn(k, row_order=1)
+    perm = index.perm().cpu().numpy()
+    valid = perm >= 0
+    assert sorted(perm[valid].tolist()) == list(range(Pt.shape[0]))
+    got = nat.u32_numpy(idx)[valid]
+    assert (got == g["knn_idx"][perm[valid]]).all()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_density_vs_golden(name, golden):
+    nat = _native()
+    g = golden(name)
+    w = _cu(g["kw_weights"].astype(np.float64)) if "kw_weights" in g else None
+    d2, idx = _cu(g["knn_d2"]), _cu(g["knn_idx"].view(np.int32))
+    raw = nat.logrho(d2, idx, int(g["k_den"]), int(g["d_intrinsic"]), weights=w)
+    ref = g["logRho_raw"].astype(np.float64)
+    got = raw.cpu().numpy().astype(np.float64)
+    fin = np.isfinite(ref)
+    assert (np.isfinite(got) == fin).all()
+    # north_star tolerance: 1e-5 relative
+    assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-5 * np.maximum(np.abs(ref[fin]), 1e-30))
+    lr = nat.normalise_(raw.clone())
+    refn = g["logRho"].astype(np.float64)
+    gotn = lr.cpu().numpy().astype(np.float64)
+    fin = np.isfinite(refn)
+    assert np.all(np.abs(gotn[fin] - refn[fin]) <= 1e-5 * np.maximum(np.abs(refn[fin]), 1.0) )
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_edges_and_order_bit_exact(name, golden):
+    nat = _native()
+    g = golden(name)
+    L = int(g["k_link"])
+    lr = _cu(g["logRho"])
+    kNN = _cu(g["kNN"].view(np.int32))
+    w, pairs = nat.make_edges(lr, kNN, L)
+    assert (w.cpu().numpy() == g["edges"]).all()
+    assert (nat.u32_numpy(pairs) == g["pairs"]).all()
+    sp, order = nat.sort_edges(w, pairs, want_order=True)
+    assert (nat.u32_numpy(order).astype(np.int64) == g["order"]).all(), "canonical order: weight desc, slot asc"
+    assert (nat.u32_numpy(sp) == g["pairs"][g["order"]]).all()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()])
+def test_rescale_vs_golden(name, golden):
+    nat = _native()
+    g = golden(name)
+    if "kw_adaptive" in g and int(g["kw_adaptive"]) == 0:
+        pytest.skip("adaptive=0")
+    P = _cu(g["P"])
+    Pt, std = nat.rescale(P)
+    ref = g["P_transform"].astype(np.float64)
+    got = Pt.cpu().numpy().astype(np.float64)
+    tol = 1e-6 if g["P"].dtype == np.float32 else 1e-13
+    assert np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), 1e-30))
+
+
+@pytest.mark.parametrize("n,d,dtype,k", [(20000, 3, np.float32, 20), (30011, 6, np.float32, 20), (5000, 2, np.float64, 9),
+                                         (12345, 6, np.float64, 20), (40000, 1, np.float32, 18), (9000, 8, np.float32, 33),
+                                         (3000, 4, np.float32, 100), (33, 3, np.float32, 5), (31, 2, np.float32, 31),
+                                         (100000, 6, np.float32, 20)])
+def test_knn_vs_oracle_random(n, d, dtype, k):
+    from oracle import oracle
+    nat = _native()
+    rng = np.random.default_rng(n + d)
+    P = np.concatenate([rng.normal(0, 1, (n // 2, d)), rng.normal(3, 0.2, (n - n // 2, d))]).astype(dtype)
+    P = np.ascontiguousarray(P[rng.permutation(n)])
+    index = nat.Index(_cu(P))
+    d2, idx, pairs = index.knn(k, count_pairs=True)
+    od2, oidx = oracle.knn(P, k)
+    assert (nat.u32_numpy(idx) == oidx).all()
+    assert (d2.cpu().numpy() == od2).all()
+    assert int(pairs.item()) >= n * min(n, 32)
