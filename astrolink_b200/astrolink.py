@@ -1,0 +1,369 @@
+"""`AstroLink(P, ...).run()` -- the reference's public interface
+(/root/reference/astrolink/astrolink.py:24-216) with its data-parallel hot path
+(transform_data -> estimate_density_and_kNN -> aggregate, :218-353) executed by
+hand-written sm_100a CUDA kernels behind the C ABI of include/astrolink_b200.h.
+
+Same constructor arguments, defaults, assertion messages, stage methods, result
+attributes and per-stage timers as the reference.  Differences, all additive:
+  * `device` / `dist` keyword arguments (defaults preserve single-GPU behaviour);
+  * `workers=-1` is accepted as documented (the reference crashes on it);
+  * the unstable edge sort at :341 is replaced by a defined total order
+    (weight descending, edge slot ascending) -- see DESIGN.md.
+There is no CPU fallback: without a CUDA device or the built library the
+constructor raises.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import stats
+
+
+class _Lazy:
+    """Attribute that lives on the GPU and is copied to a numpy array the first
+    time host code asks for it (P_transform, kNN are scratch in the reference
+    and usually never read by the user; results are fetched once)."""
+
+    def __init__(self, name, as_uint32=False):
+        self.name = name
+        self.dev = "_d_" + name
+        self.host = "_h_" + name
+        self.as_uint32 = as_uint32
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        h = obj.__dict__.get(self.host)
+        if h is not None:
+            return h
+        d = obj.__dict__.get(self.dev)
+        if d is None:
+            raise AttributeError(f"'AstroLink' object has no attribute '{self.name}'")
+        h = d.detach().cpu().numpy()
+        if self.as_uint32:
+            h = h.view(np.uint32)
+        obj.__dict__[self.host] = h
+        return h
+
+    def __set__(self, obj, value):
+        obj.__dict__.pop(self.dev, None)
+        obj.__dict__[self.host] = value
+
+    def __delete__(self, obj):
+        found = obj.__dict__.pop(self.dev, None) is not None
+        found = (obj.__dict__.pop(self.host, None) is not None) or found
+        if not found:
+            raise AttributeError(self.name)
+
+
+class AstroLink:
+    """Drop-in for the reference class (constructor: astrolink.py:132-176)."""
+
+    P_transform = _Lazy("P_transform")
+    kNN = _Lazy("kNN", as_uint32=True)
+    logRho = _Lazy("logRho")
+    ordering = _Lazy("ordering", as_uint32=True)
+    groups = _Lazy("groups", as_uint32=True)
+    prominences = _Lazy("prominences")
+
+    def __init__(self, P, d_intrinsic=None, weights=None, k_den=20, adaptive=1, S='auto', k_link='auto', h_style=1,
+                 workers=8, verbose=0, device=None, dist=None):
+        # Input Data
+        check_P = isinstance(P, np.ndarray) and len(P.shape) == 2
+        assert check_P, "Input data 'P' needs to be a 2D numpy array!"
+        self.P = P
+        self.n_samples, self.d_features = self.P.shape
+
+        check_d_intrinsic = d_intrinsic is None or (isinstance(d_intrinsic, int) and 1 <= d_intrinsic <= self.d_features)
+        assert check_d_intrinsic, "Parameter 'd_intrinsic' must be None or an integer between 1 and the number of features in 'P'!"
+        self.d_intrinsic = d_intrinsic if d_intrinsic is not None else self.d_features
+
+        check_weights = weights is None or (isinstance(weights, np.ndarray) and len(weights.shape) == 1 and weights.size == self.n_samples)
+        assert check_weights, "Parameter 'weights' must be None or a 1D numpy array with the same length as the number of samples in 'P'!"
+        self.weights = weights
+
+        check_k_den = int(k_den) == k_den and k_den <= self.n_samples
+        assert check_k_den, "Parameter 'k_den' must be an integer less than P.shape[0]!"
+        self.k_den = int(k_den)
+
+        check_adaptive = adaptive in [0, 1]
+        assert check_adaptive, "Parameter 'adaptive' must be set as either '0' or '1'!"
+        self.adaptive = adaptive
+
+        check_S = S == 'auto' or S <= 38.44939448087599
+        assert check_S, "Parameter 'S' must be set to 'auto' or be less than or equal to 38.44939448087599 due to the limiting precision of the (inverse) survival functions from scipy.stats!"
+        self.S = S
+
+        check_k_link = k_link == 'auto' or 1 < k_link <= self.k_den
+        assert check_k_link, "Parameter 'k_link' needs to be an integer satisfying 1 < k_link <= k_den or 'auto'!"
+        if k_link == 'auto':
+            # empirical fit of the reference (astrolink.py:164)
+            self.k_link = max(int(np.ceil(11.97 * self.d_intrinsic ** (-2.23) - 22.97 * self.k_den ** (-0.57) + 10.03)), 7)
+        else:
+            self.k_link = k_link
+
+        check_h_style = h_style in [0, 1]
+        assert check_h_style, "Parameter 'h_style' must be set as either '0' or '1'!"
+        self.h_style = h_style
+
+        check_workers = 1 <= workers or workers == -1
+        assert check_workers, f"Parameter 'workers' must be set as either '-1' or needs to be an integer that is >= 1 (values > N_cpu will be set to N_cpu)"
+        # host threads only matter for the SciPy fit; the hot path runs on the GPU
+        self.workers = workers
+        self.verbose = verbose
+
+        # ---- additions
+        nat.require_cuda()
+        nat.lib()
+        assert self.n_samples < 2 ** 31 - 1, "astrolink_b200 supports up to 2**31 - 2 points (uint32 indices)"
+        assert self.P.dtype in (np.float32, np.float64), "astrolink_b200 supports float32 / float64 input"
+        assert self.d_features <= 8, "astrolink_b200 supports up to 8 features in this release"
+        assert self.k_den <= 128, "astrolink_b200 supports k_den <= 128 in this release"
+        self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._dist = dist
+        self._gpu_launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _printFunction(self, message, returnLine=True, urgent=False):
+        if self.verbose or urgent:
+            if returnLine:
+                print(f"AstroLink: {message}\r", end='')
+            else:
+                print(f"AstroLink: {message}")
+
+    def _to_device(self, a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(self._device, non_blocking=True)
+
+    def _dev(self, name):
+        """Device tensor behind a lazy attribute (uploading a user-injected numpy array)."""
+        d = self.__dict__.get("_d_" + name)
+        if d is None:
+            h = self.__dict__.get("_h_" + name)
+            if h is None:
+                raise AttributeError(f"'{name}' has not been created yet")
+            if h.dtype == np.uint32:
+                h = h.view(np.int32)
+            d = self._to_device(h)
+            self.__dict__["_d_" + name] = d
+        return d
+
+    def _set_dev(self, name, tensor):
+        self.__dict__.pop("_h_" + name, None)
+        self.__dict__["_d_" + name] = tensor
+
+    def __getstate__(self):
+        # picklable like the reference object: device tensors become numpy arrays
+        state = {}
+        for k, v in self.__dict__.items():
+            if k.startswith("_d_") or k in ("_dist", "_device"):
+                continue
+            state[k] = v
+        for name in ("P_transform", "kNN", "logRho", "ordering", "groups", "prominences"):
+            if ("_d_" + name) in self.__dict__ and ("_h_" + name) not in self.__dict__:
+                state["_h_" + name] = getattr(self, name)
+        state["_device"] = str(self._device)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._device = torch.device(state.get("_device", "cuda"))
+        self._dist = None
+
+    # ------------------------------------------------------------------ run
+    def run(self):
+        """transform_data, estimate_density_and_kNN, aggregate, compute_significances,
+        extract_clusters (astrolink.py:183-216)."""
+        self._printFunction(f"Started             | {time.strftime('%Y-%m-%d %H:%M:%S')}", returnLine=False)
+        begin = time.perf_counter()
+        self.transform_data()
+        self.estimate_density_and_kNN()
+        self.aggregate()
+        if self._is_result_rank():
+            self.compute_significances()
+            self.extract_clusters()
+        else:
+            self._regrTime = self._rejTime = 0.0
+        self._totalTime = time.perf_counter() - begin
+        if self.verbose > 1:
+            self._printFunction(f"Transformation time | {100*self._transformTime/self._totalTime:.2f}%    ", returnLine=False)
+            self._printFunction(f"kNN query time      | {100*self._logRhoTime/self._totalTime:.2f}%       ", returnLine=False)
+            self._printFunction(f"Aggregation time    | {100*self._aggregateTime/self._totalTime:.2f}%    ", returnLine=False)
+            self._printFunction(f"Regression time     | {100*self._regrTime/self._totalTime:.2f}%         ", returnLine=False)
+            self._printFunction(f"Rejection time      | {100*self._rejTime/self._totalTime:.2f}%          ", returnLine=False)
+        self._printFunction(f"Completed           | {time.strftime('%Y-%m-%d %H:%M:%S')}       ", returnLine=False)
+
+    def _world(self):
+        d = self._dist
+        if d is None:
+            return 0, 1
+        return d.get_rank(), d.get_world_size()
+
+    def _is_result_rank(self):
+        return self._world()[0] == 0
+
+    # ------------------------------------------------------------------ a1
+    def transform_data(self):
+        """adaptive=1: every feature divided by its standard deviation; adaptive=0:
+        untouched (astrolink.py:218-234).  Creates `P_transform`."""
+        start = time.perf_counter()
+        with torch.cuda.device(self._device):
+            dP = self._to_device(self.P)
+            if self.adaptive:
+                if self.verbose > 1:
+                    self._printFunction('Transforming data...      ')
+                Pt, _ = nat.rescale(dP)
+                self._gpu_launches += 5
+            else:
+                Pt = dP
+            self._set_dev("P_transform", Pt)
+        self._transformTime = time.perf_counter() - start
+
+    # ------------------------------------------------------------------ a2-a7
+    def estimate_density_and_kNN(self):
+        """k_den nearest neighbours of every point, Epanechnikov/balloon log-density,
+        min-max normalisation; keeps the k_link nearest (astrolink.py:245-291).
+        Requires `P_transform`; creates `logRho`, `kNN`; deletes `P_transform`."""
+        if self.verbose > 1:
+            self._printFunction('Computing densities...    ')
+        start = time.perf_counter()
+        with torch.cuda.device(self._device):
+            Pt = self._dev("P_transform")
+            if not Pt.is_contiguous():
+                Pt = Pt.contiguous()
+            n, K, L = self.n_samples, self.k_den, self.k_link
+            index = nat.Index(Pt)
+            self._index_positions = index.positions
+            w = None
+            if self.weights is not None:
+                w = self._to_device(np.asarray(self.weights, dtype=np.float64))
+            rank, world = self._world()
+            if world == 1:
+                d2, idx = index.knn(K, row_order=0)
+                raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
+                kNN = idx[:, :L].contiguous() if L < K else idx
+                del d2
+            else:
+                raw, kNN = self._sharded_knn(index, w, rank, world)
+            lr = nat.normalise_(raw)
+            self._gpu_launches += 6
+            self._set_dev("logRho", lr)
+            self._set_dev("kNN", kNN)
+            del self.P_transform
+        self._logRhoTime = time.perf_counter() - start
+
+    def _sharded_knn(self, index, w, rank, world):
+        """Query-sharded kNN: every rank searches a contiguous block of index
+        positions against the replicated point set, then the k_link neighbour
+        lists and raw densities are all-gathered over NCCL."""
+        from . import dist as adist
+        n, K, L = self.n_samples, self.k_den, self.k_link
+        lo, hi, per = adist.shard_positions(index.positions, rank, world, nat.LEAF)
+        d2, idx = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1)
+        raw_s = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
+        del d2
+        knn_s = torch.full((per, L), -1, dtype=torch.int32, device=self._device)
+        knn_s[:hi - lo] = idx[:, :L]
+        raw_p = torch.full((per,), float("inf"), dtype=raw_s.dtype, device=self._device)
+        raw_p[:hi - lo] = raw_s
+        knn_all = torch.empty((per * world, L), dtype=torch.int32, device=self._device)
+        raw_all = torch.empty((per * world,), dtype=raw_s.dtype, device=self._device)
+        self._dist.all_gather_into_tensor(knn_all, knn_s)
+        self._dist.all_gather_into_tensor(raw_all, raw_p)
+        # back to original point order
+        sel = adist.gathered_rows(index.positions, world, nat.LEAF, self._device)
+        perm = index.perm()
+        kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
+        raw = torch.empty((n,), dtype=raw_s.dtype, device=self._device)
+        nat.scatter_rows(knn_all[sel].contiguous(), perm, kNN)
+        nat.scatter_rows(raw_all[sel].contiguous().view(-1, 1), perm, raw.view(-1, 1))
+        return raw, kNN
+
+    # ------------------------------------------------------------------ a8-a11
+    def aggregate(self):
+        """Edges between every point and its k_link neighbours weighted by the
+        smaller logRho, sorted descending, aggregated into the ordered list with
+        groups and prominences (astrolink.py:315-353).  Requires `logRho`, `kNN`;
+        creates `ordering`, `groups`, `prominences`; deletes `kNN`.  Runs on rank 0
+        when sharded."""
+        if self.verbose > 1:
+            self._printFunction('Aggregating points...        ')
+        start = time.perf_counter()
+        if not self._is_result_rank():
+            del self.kNN
+            self._aggregateTime = time.perf_counter() - start
+            return
+        with torch.cuda.device(self._device):
+            lr = self._dev("logRho")
+            kNN = self._dev("kNN")
+            w, pairs = nat.make_edges(lr, kNN, self.k_link)
+            del self.kNN
+            sorted_pairs = nat.sort_edges(w, pairs)
+            del w, pairs
+            ordering, groups, prom = nat.aggregate(lr, sorted_pairs)
+            del sorted_pairs
+            self._gpu_launches += 5
+            self._set_dev("ordering", ordering)
+            self._set_dev("groups", groups)
+            self._set_dev("prominences", prom)
+            # results the host needs: small ones now, the big ones while the fit runs
+            self._fetch_results()
+        self._aggregateTime = time.perf_counter() - start
+
+    def _fetch_results(self):
+        side = torch.cuda.Stream(device=self._device)
+        side.wait_stream(torch.cuda.current_stream())
+        bufs = {}
+        with torch.cuda.stream(side):
+            for name in ("groups", "prominences", "ordering", "logRho"):
+                d = self.__dict__["_d_" + name]
+                h = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
+                h.copy_(d, non_blocking=True)
+                bufs[name] = h
+        self._pending = (side, bufs)
+
+    def _finish_fetch(self, names):
+        pend = self.__dict__.get("_pending")
+        if pend is None:
+            return
+        side, bufs = pend
+        side.synchronize()
+        for name in list(bufs):
+            h = bufs.pop(name).numpy()
+            if name in ("groups", "ordering"):
+                h = h.view(np.uint32)
+            self.__dict__["_h_" + name] = h
+        self._pending = None
+
+    # ------------------------------------------------------------------ host statistics
+    def compute_significances(self):
+        """Beta model of the prominences fitted by minimising the Wasserstein-1
+        distance; significances through the standard normal (astrolink.py:828-860).
+        Requires `prominences`; creates `groups_sigs`, `pFit`."""
+        if self.verbose > 1:
+            self._printFunction('Finding significances...  ')
+        start = time.perf_counter()
+        self._finish_fetch(("groups", "prominences"))
+        prom = self.prominences
+        self.pFit, ok = stats.fit_prominence_model(prom[:, 1])
+        if not ok:
+            self._printFunction('[Warning] Prominence model fitting failed to converge!', returnLine=False, urgent=True)
+        self.groups_sigs = stats.significances_of(prom, self.pFit)
+        self._regrTime = time.perf_counter() - start
+
+    def extract_clusters(self):
+        """Groups at least S-sigma significant become clusters; hierarchy per h_style
+        (astrolink.py:909-980).  Requires `groups`, `groups_sigs`; creates `clusters`,
+        `ids`, `significances`.  Like the reference, S='auto' is replaced by its value."""
+        if self.verbose > 1:
+            self._printFunction('Finding clusters...       ')
+        start = time.perf_counter()
+        self._finish_fetch(())
+        if self.S == 'auto':
+            self.S = stats.auto_threshold(self.prominences.shape[0])
+        self.clusters, self.ids, self.significances = stats.extract(self.groups, self.groups_sigs, self.S, self.h_style,
+                                                                    self.n_samples)
+        self._rejTime = time.perf_counter() - start

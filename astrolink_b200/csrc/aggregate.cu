@@ -1,7 +1,122 @@
-// placeholder while the aggregation pass is being written
+// CUDA executor + C entry point of the aggregation pass (algorithm in
+// aggregate_impl.h): replaces _aggregate_njit_float{32,64}_uint32
+// (reference astrolink/astrolink.py:384-604).
+#include <cub/cub.cuh>
+
+#include "aggregate_impl.h"
 #include "common.cuh"
-extern "C" size_t al_aggregate_workspace_bytes(int dtype, int64_t n, int64_t E) { (void)dtype; (void)n; (void)E; return 256; }
-extern "C" int al_aggregate(const void*, int, const uint32_t*, int64_t, int64_t, uint32_t*, uint32_t*, void*, int64_t*, void*, size_t, void*) {
-    al_set_error("al_aggregate: not implemented yet");
-    return AL_EINTERNAL;
+
+template <class Tag, class F>
+__global__ void __launch_bounds__(256) agg_kernel(i64 n, F f) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) f(i);
+}
+
+__global__ void agg_fill_kernel(u32* p, u32 v, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+struct CudaExec {
+    cudaStream_t st;
+    cudaError_t err = cudaSuccess;
+    long launches = 0;
+
+    void note(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+
+    template <class Tag, class F>
+    void launch(i64 n, F f) {
+        if (n <= 0) return;
+        i64 g = (n + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        agg_kernel<Tag, F><<<(unsigned)g, 256, 0, st>>>(n, f);
+        note(cudaGetLastError());
+        launches++;
+    }
+    void fill_u32(u32* p, u32 v, i64 n) {
+        if (n <= 0) return;
+        if (v == 0u || v == 0xffffffffu) note(cudaMemsetAsync(p, v == 0u ? 0 : 0xff, (size_t)n * 4, st));
+        else {
+            i64 g = (n + 255) / 256;
+            if (g > 148 * 16) g = 148 * 16;
+            agg_fill_kernel<<<(unsigned)g, 256, 0, st>>>(p, v, n);
+            note(cudaGetLastError());
+        }
+    }
+    u32 read_u32(const u32* p) {
+        u32 v = 0;
+        note(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, st));
+        note(cudaStreamSynchronize(st));
+        return v;
+    }
+    // out[i] = sum of in[0..i); returns the total
+    i64 exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar) {
+        if (n <= 0) return 0;
+        const size_t mk = ar.mark();
+        size_t tb = 0;
+        note(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return -1; }
+        u32 last_in = read_u32(in + (n - 1));      // read before the scan: `out` may alias later users of `in`
+        note(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, st));
+        u32 last_out = read_u32(out + (n - 1));
+        ar.reset(mk);
+        return (i64)last_out + (i64)last_in;
+    }
+    void inclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar) {
+        if (n <= 0) return;
+        const size_t mk = ar.mark();
+        size_t tb = 0;
+        note(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, n, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DeviceScan::InclusiveSum(tmp, tb, in, out, n, st));
+        note(cudaStreamSynchronize(st));   // tmp is released below
+        ar.reset(mk);
+    }
+    void sort_pairs_u64_u32(const u64* k_in, u64* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena& ar) {
+        if (n <= 0) return;
+        const size_t mk = ar.mark();
+        size_t tb = 0;
+        note(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
+        note(cudaStreamSynchronize(st));
+        ar.reset(mk);
+    }
+    void sync() { note(cudaStreamSynchronize(st)); }
+};
+
+extern "C" size_t al_aggregate_workspace_bytes(int dtype, int64_t n, int64_t E) {
+    return agg::workspace_bound((size_t)n, (size_t)E, dtype == AL_F64 ? 8 : 4);
+}
+
+extern "C" int al_aggregate(const void* logrho, int dtype, const uint32_t* sorted_pairs, int64_t n, int64_t E, uint32_t* ordering_out,
+                            uint32_t* groups_out, void* prominences_out, int64_t* n_groups_host, void* ws, size_t ws_bytes,
+                            void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_aggregate: bad dtype");
+    AL_REQUIRE(n >= 2 && n < 0x7fffffffll && E >= 1 && E < 0xffffffffll, AL_EINVAL, "al_aggregate: n or E out of range");
+    AL_REQUIRE(n_groups_host != nullptr, AL_EINVAL, "al_aggregate: n_groups_host is NULL");
+    CudaExec x;
+    x.st = (cudaStream_t)stream;
+    AggArena ar(ws, ws_bytes);
+    int rc;
+    if (dtype == AL_F32)
+        rc = agg::run<CudaExec, float>(x, ar, (const float*)logrho, sorted_pairs, n, E, false, ordering_out, groups_out,
+                                       (float*)prominences_out, n_groups_host);
+    else
+        rc = agg::run<CudaExec, double>(x, ar, (const double*)logrho, sorted_pairs, n, E, true, ordering_out, groups_out,
+                                        (double*)prominences_out, n_groups_host);
+    if (x.err != cudaSuccess) {
+        al_set_error("al_aggregate: CUDA error: %s", cudaGetErrorString(x.err));
+        return AL_ECUDA;
+    }
+    if (rc == -2) {
+        al_set_error("al_aggregate: workspace too small (%zu bytes given, %zu used before failing)", ws_bytes, ar.high);
+        return AL_ENOMEM;
+    }
+    if (rc != 0) {
+        al_set_error("al_aggregate: internal consistency check %d failed (is every point an endpoint of some edge?)", rc);
+        return AL_EINTERNAL;
+    }
+    return AL_OK;
 }

@@ -1,0 +1,61 @@
+// TEST INFRASTRUCTURE ONLY -- never loaded by the product package.
+//
+// Serial host executor for the aggregation algorithm in
+// astrolink_b200/csrc/aggregate_impl.h.  It runs every data-parallel pass of
+// that algorithm as a plain loop (one valid interleaving of the GPU threads), so
+// the LOGIC of the parallel formulation can be checked against the oracle on a
+// machine without a GPU (`pytest -m "not gpu"`).  It says nothing about races
+// or CUDA specifics; those are covered by the -m gpu parity tests.
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "../../astrolink_b200/csrc/aggregate_impl.h"
+
+struct HostExec {
+    long launches = 0;
+    template <class Tag, class F>
+    void launch(i64 n, F f) {
+        for (i64 i = 0; i < n; i++) f(i);
+        launches++;
+    }
+    void fill_u32(u32* p, u32 v, i64 n) { for (i64 i = 0; i < n; i++) p[i] = v; }
+    u32 read_u32(const u32* p) { return *p; }
+    i64 exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&) {
+        i64 s = 0;
+        for (i64 i = 0; i < n; i++) { u32 v = in[i]; out[i] = (u32)s; s += v; }
+        return s;
+    }
+    void inclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&) {
+        u32 s = 0;
+        for (i64 i = 0; i < n; i++) { s += in[i]; out[i] = s; }
+    }
+    void sort_pairs_u64_u32(const u64* k_in, u64* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena&) {
+        std::vector<i64> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        const u64 mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+        std::stable_sort(idx.begin(), idx.end(), [&](i64 a, i64 b) { return (k_in[a] & mask) < (k_in[b] & mask); });
+        for (i64 i = 0; i < n; i++) { k_out[i] = k_in[idx[i]]; v_out[i] = v_in[idx[i]]; }
+    }
+    void sync() {}
+};
+
+template <typename T>
+static i64 run_host(const T* logrho, const u32* sorted_pairs, i64 n, i64 E, bool quirk, u32* ordering, u32* groups, T* prom) {
+    size_t bytes = agg::workspace_bound((size_t)n, (size_t)E, sizeof(T));
+    void* ws = malloc(bytes);
+    AggArena ar(ws, bytes);
+    HostExec x;
+    i64 G = 0;
+    int rc = agg::run<HostExec, T>(x, ar, logrho, sorted_pairs, n, E, quirk, ordering, groups, prom, &G);
+    free(ws);
+    return rc == 0 ? G : (i64)rc;
+}
+
+extern "C" i64 hostsim_aggregate_f32(const float* logrho, const u32* sorted_pairs, i64 n, i64 E, u32* ordering, u32* groups, float* prom) {
+    return run_host<float>(logrho, sorted_pairs, n, E, false, ordering, groups, prom);
+}
+extern "C" i64 hostsim_aggregate_f64(const double* logrho, const u32* sorted_pairs, i64 n, i64 E, u32* ordering, u32* groups, double* prom) {
+    return run_host<double>(logrho, sorted_pairs, n, E, true, ordering, groups, prom);
+}

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names
+from tests.conftest import golden_names
 
 pytestmark = pytest.mark.gpu
 
