@@ -43,6 +43,7 @@ _SIGS = {
     "al_aggregate": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
     "al_fp32_peak_tflops": (_int, [_vp, _vp]),
+    "al_launch_count": (_i64, []),
 }
 
 
@@ -240,6 +241,10 @@ def fp32_peak_tflops():
     v = ctypes.c_double(0.0)
     _check(L.al_fp32_peak_tflops(ctypes.byref(v), _stream()), "al_fp32_peak_tflops")
     return float(v.value)
+
+
+def launch_count():
+    return int(lib().al_launch_count())
 
 
 def u32_numpy(t):

@@ -124,7 +124,23 @@ class AstroLink:
         assert self.k_den <= 128, "astrolink_b200 supports k_den <= 128 in this release"
         self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._dist = dist
-        self._gpu_launches = 0
+        self._events = {}          # stage -> (start, end) CUDA events on the launching stream
+        self._knn_pairs = None     # device counter of (query, candidate) distance evaluations
+
+    def _use_device_input(self, dP):
+        """Benchmark hook: P is already resident in HBM (same values as self.P)."""
+        assert dP.shape == self.P.shape and dP.is_cuda
+        self._d_P_in = dP
+
+    def _stage(self, name):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._events[name] = ev
+        return ev
+
+    def stage_ms(self):
+        """Device time of each stage of the last run (CUDA events), in ms."""
+        torch.cuda.synchronize(self._device)
+        return {k: a.elapsed_time(b) for k, (a, b) in self._events.items()}
 
     # ------------------------------------------------------------------ helpers
     def _printFunction(self, message, returnLine=True, urgent=False):
@@ -159,7 +175,7 @@ class AstroLink:
         # picklable like the reference object: device tensors become numpy arrays
         state = {}
         for k, v in self.__dict__.items():
-            if k.startswith("_d_") or k in ("_dist", "_device"):
+            if k.startswith("_d_") or k in ("_dist", "_device", "_events", "_knn_pairs", "_pending"):
                 continue
             state[k] = v
         for name in ("P_transform", "kNN", "logRho", "ordering", "groups", "prominences"):
@@ -172,6 +188,8 @@ class AstroLink:
         self.__dict__.update(state)
         self._device = torch.device(state.get("_device", "cuda"))
         self._dist = None
+        self._events = {}
+        self._knn_pairs = None
 
     # ------------------------------------------------------------------ run
     def run(self):
@@ -211,14 +229,18 @@ class AstroLink:
         untouched (astrolink.py:218-234).  Creates `P_transform`."""
         start = time.perf_counter()
         with torch.cuda.device(self._device):
-            dP = self._to_device(self.P)
+            dP = self.__dict__.get("_d_P_in")
+            if dP is None:
+                dP = self._to_device(self.P)
+            a, b = self._stage("rescale")
+            a.record()
             if self.adaptive:
                 if self.verbose > 1:
                     self._printFunction('Transforming data...      ')
                 Pt, _ = nat.rescale(dP)
-                self._gpu_launches += 5
             else:
                 Pt = dP
+            b.record()
             self._set_dev("P_transform", Pt)
         self._transformTime = time.perf_counter() - start
 
@@ -235,21 +257,31 @@ class AstroLink:
             if not Pt.is_contiguous():
                 Pt = Pt.contiguous()
             n, K, L = self.n_samples, self.k_den, self.k_link
+            a, b = self._stage("index_build")
+            a.record()
             index = nat.Index(Pt)
+            b.record()
             self._index_positions = index.positions
             w = None
             if self.weights is not None:
                 w = self._to_device(np.asarray(self.weights, dtype=np.float64))
             rank, world = self._world()
             if world == 1:
-                d2, idx = index.knn(K, row_order=0)
+                a, b = self._stage("knn")
+                a.record()
+                d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True)
+                b.record()
+                a, b = self._stage("density")
+                a.record()
                 raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
                 kNN = idx[:, :L].contiguous() if L < K else idx
                 del d2
             else:
                 raw, kNN = self._sharded_knn(index, w, rank, world)
+                a, b = self._stage("density")
+                a.record()
             lr = nat.normalise_(raw)
-            self._gpu_launches += 6
+            b.record()
             self._set_dev("logRho", lr)
             self._set_dev("kNN", kNN)
             del self.P_transform
@@ -262,7 +294,10 @@ class AstroLink:
         from . import dist as adist
         n, K, L = self.n_samples, self.k_den, self.k_link
         lo, hi, per = adist.shard_positions(index.positions, rank, world, nat.LEAF)
-        d2, idx = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1)
+        a, b = self._stage("knn")
+        a.record()
+        d2, idx, self._knn_pairs = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1, count_pairs=True)
+        b.record()
         raw_s = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
         del d2
         knn_s = torch.full((per, L), -1, dtype=torch.int32, device=self._device)
@@ -271,8 +306,11 @@ class AstroLink:
         raw_p[:hi - lo] = raw_s
         knn_all = torch.empty((per * world, L), dtype=torch.int32, device=self._device)
         raw_all = torch.empty((per * world,), dtype=raw_s.dtype, device=self._device)
+        a, b = self._stage("all_gather")
+        a.record()
         self._dist.all_gather_into_tensor(knn_all, knn_s)
         self._dist.all_gather_into_tensor(raw_all, raw_p)
+        b.record()
         # back to original point order
         sel = adist.gathered_rows(index.positions, world, nat.LEAF, self._device)
         perm = index.perm()
@@ -299,13 +337,21 @@ class AstroLink:
         with torch.cuda.device(self._device):
             lr = self._dev("logRho")
             kNN = self._dev("kNN")
+            a, b = self._stage("edges")
+            a.record()
             w, pairs = nat.make_edges(lr, kNN, self.k_link)
+            b.record()
             del self.kNN
+            a, b = self._stage("sort")
+            a.record()
             sorted_pairs = nat.sort_edges(w, pairs)
+            b.record()
             del w, pairs
+            a, b = self._stage("aggregate")
+            a.record()
             ordering, groups, prom = nat.aggregate(lr, sorted_pairs)
+            b.record()
             del sorted_pairs
-            self._gpu_launches += 5
             self._set_dev("ordering", ordering)
             self._set_dev("groups", groups)
             self._set_dev("prominences", prom)

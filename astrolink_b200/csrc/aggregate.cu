@@ -106,6 +106,7 @@ extern "C" int al_aggregate(const void* logrho, int dtype, const uint32_t* sorte
     else
         rc = agg::run<CudaExec, double>(x, ar, (const double*)logrho, sorted_pairs, n, E, true, ordering_out, groups_out,
                                         (double*)prominences_out, n_groups_host);
+    al_count_launches(x.launches);
     if (x.err != cudaSuccess) {
         al_set_error("al_aggregate: CUDA error: %s", cudaGetErrorString(x.err));
         return AL_ECUDA;

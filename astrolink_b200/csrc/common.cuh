@@ -12,6 +12,8 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 
 void al_set_error(const char* fmt, ...);
+// number of kernels this library launched (its own kernels; CUB's internal ones are not counted)
+void al_count_launches(long n);
 
 #define AL_CUDA(expr)                                                                      \
     do {                                                                                   \
@@ -22,7 +24,11 @@ void al_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
-#define AL_CHECK_LAUNCH() AL_CUDA(cudaGetLastError())
+#define AL_CHECK_LAUNCH()            \
+    do {                             \
+        al_count_launches(1);        \
+        AL_CUDA(cudaGetLastError()); \
+    } while (0)
 
 #define AL_REQUIRE(cond, code, ...)      \
     do {                                 \

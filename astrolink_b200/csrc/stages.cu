@@ -24,6 +24,11 @@ void al_set_error(const char* fmt, ...) {
 extern "C" const char* al_last_error(void) { return g_err; }
 extern "C" int al_version(void) { return 1; }
 
+#include <atomic>
+static std::atomic<long> g_launches{0};
+void al_count_launches(long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t al_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
 constexpr int RS_MAXD = 16;
 constexpr int RS_BLOCKS = 592;   // 4 x 148 SMs
 constexpr int RS_THREADS = 256;
@@ -238,9 +243,11 @@ extern "C" int al_minmax(const void* x, int dtype, int64_t n, void* minmax_out, 
     if (dtype == AL_F32) {
         minmax_partial_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, n, (float*)partial);
         minmax_final_kernel<float><<<1, 32, 0, st>>>((const float*)partial, blocks, (float*)minmax_out);
+        al_count_launches(1);
     } else {
         minmax_partial_kernel<double><<<blocks, 256, 0, st>>>((const double*)x, n, partial);
         minmax_final_kernel<double><<<1, 32, 0, st>>>(partial, blocks, (double*)minmax_out);
+        al_count_launches(1);
     }
     AL_CHECK_LAUNCH();
     return AL_OK;

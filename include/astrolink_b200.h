@@ -133,6 +133,9 @@ int al_aggregate(const void* logrho, int dtype, const uint32_t* sorted_pairs, in
  * perm == 0xffffffff; elem_bytes is 4 or 8. */
 int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int cols, int src_stride,
                     int dst_stride, int elem_bytes, void* dst, void* stream);
+/* kernels launched by this library so far in this process (its own kernels; CUB's
+ * internal launches are not counted). */
+int64_t al_launch_count(void);
 /* measured FP32 FMA issue rate of this GPU in TFLOP/s (2 flop per FMA); used as
  * the roofline denominator of the kNN kernel.  Synchronous. */
 int al_fp32_peak_tflops(double* tflops_host, void* stream);
