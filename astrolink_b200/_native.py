@@ -147,7 +147,7 @@ class Index:
         rows = self.n if row_order == 0 else pos_end - pos_begin
         idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
         d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
-        pairs = torch.zeros(1, dtype=torch.int64, device=self.device) if count_pairs else None
+        pairs = torch.zeros(8, dtype=torch.int64, device=self.device) if count_pairs else None
         ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)
         _check(L.al_knn(_ptr(self.buf), pos_begin, pos_end, k, row_order, _ptr(idx), _ptr(d2), _ptr(pairs), _ptr(ws), ws.numel(),
                         _stream()), "al_knn")

@@ -49,12 +49,12 @@ extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int
     p.row_order = row_order;
     p.idx_out = idx_out;
     p.d2_out = d2_out;
-    p.pairs = pairs_evaluated;
+    p.stats = pairs_evaluated;
     cudaStream_t st = (cudaStream_t)stream;
     if (h.dtype == AL_F32) {
-        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride);
+        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride, k, h.d);
         return g_knn_f32[h.d - 1](p, st);
     }
-    p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride);
+    p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride, k, h.d);
     return g_knn_f64[h.d - 1](p, st);
 }

@@ -5,4 +5,4 @@
 #define KNN_CAT2(a, b, c) a##b##_d##c
 #define KNN_CAT(a, b, c) KNN_CAT2(a, b, c)
 
-int KNN_CAT(knn_launch_, KNN_TNAME, KNN_D)(const KnnParams& p, cudaStream_t st) { return knn_dispatch_k<KNN_T, KNN_D>(p, st); }
+int KNN_CAT(knn_launch_, KNN_TNAME, KNN_D)(const KnnParams& p, cudaStream_t st) { return launch_knn<KNN_T, KNN_D>(p, st); }

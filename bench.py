@@ -231,7 +231,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (kNN), from the last timed resident run
     stage = c.stage_ms()
-    pairs = int(c._knn_pairs.item())
+    pairs = int(c._knn_pairs[0].item())
     if D is not None:
         import torch.distributed as td
         t = torch.tensor([float(pairs), stage["knn"]], dtype=torch.float64, device=dev)

@@ -76,8 +76,10 @@ const uint32_t* al_index_perm(const void* index);
  * row_order 1: row of index position p written at row p - pos_begin
  *              ([pos_end - pos_begin][k] arrays; padding rows are filled with
  *              0xffffffff / +inf).
- * pairs_evaluated (device uint64, may be NULL) is incremented by the number of
- * (query, candidate) distance evaluations, for roofline accounting. */
+ * pairs_evaluated (device uint64[8], may be NULL) accumulates kernel statistics
+ * for roofline accounting: [0] (query, candidate) distance evaluations,
+ * [1] tiles fetched, [2] tiles evaluated, [3] lanes needing a tile, [4] queue
+ * pushes, [5] top-k insertions, [6] merge iterations, [7] chunks on the push path. */
 size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k);
 int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order,
            uint32_t* idx_out, void* d2_out, unsigned long long* pairs_evaluated,

@@ -1,0 +1,22 @@
+"""Profiling driver: builds the index on a reduced C4 workload and runs the kNN
+kernel (and optionally the whole pipeline) so ncu can capture it."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from astrolink_b200 import synth, _native as nat
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+P = synth.halo6d(n, seed=4, n_sub=256, nested=True)
+dP = torch.from_numpy(P).cuda()
+Pt, _ = nat.rescale(dP)
+index = nat.Index(Pt)
+for _ in range(3):
+    d2, idx, pairs = index.knn(20, count_pairs=True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); d2, idx, pairs = index.knn(20, count_pairs=True); e1.record(); torch.cuda.synchronize()
+st = pairs.cpu().numpy().astype(float)
+ms = e0.elapsed_time(e1)
+print(f"n={n} knn {ms:.3f} ms  pairs/query {st[0]/n:.0f}  tiles/leaf loaded {st[1]/(n/32):.1f} evaluated {st[2]/(n/32):.1f}  "
+      f"needy lanes/loaded tile {st[3]/max(st[1],1):.2f}  pushes/query {st[4]/n:.1f} inserts/query {st[5]/n:.1f}  "
+      f"flush iters/leaf {st[6]/(n/32):.1f}  slow chunks/eval tile {st[7]/max(st[2],1):.2f}  TFLOP/s {st[0]*18/ms/1e9:.2f}")
