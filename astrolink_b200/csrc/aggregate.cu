@@ -5,6 +5,8 @@
 
 #include "aggregate_impl.h"
 #include "common.cuh"
+#include <stdlib.h>
+#include <time.h>
 
 template <class Tag, class F>
 __global__ void __launch_bounds__(256) agg_kernel(i64 n, F f) {
@@ -84,6 +86,42 @@ struct CudaExec {
         ar.reset(mk);
     }
     void sync() { note(cudaStreamSynchronize(st)); }
+    void segmented_inclusive_scan(SegItem* items, i64 n, AggArena& ar) {
+        if (n <= 0) return;
+        const size_t mk = ar.mark();
+        size_t tb = 0;
+        note(cub::DeviceScan::InclusiveScan(nullptr, tb, items, items, SegOp(), n, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DeviceScan::InclusiveScan(tmp, tb, items, items, SegOp(), n, st));
+        note(cudaStreamSynchronize(st));
+        ar.reset(mk);
+    }
+    char lvl_name[64];
+    void phase_level(const char* base, int l, i64 m, i64 N) {
+        if (!prof) return;
+        snprintf(lvl_name, sizeof(lvl_name), "%s-%02d m=%lld N=%lld", base, l, (long long)m, (long long)N);
+        phase(lvl_name);
+    }
+    // optional phase timing (AL_PROFILE=1): wall time between phase markers, stream synchronised
+    bool prof = false;
+    const char* cur = nullptr;
+    double t0 = 0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    void phase(const char* name) {
+        if (!prof) return;
+        cudaStreamSynchronize(st);
+        double t = now();
+        if (cur) fprintf(stderr, "[al_aggregate] %-36s %8.3f ms  (launches so far %ld)\n", cur, t - t0, launches);
+        static char keep[64];
+        snprintf(keep, sizeof(keep), "%s", name);
+        cur = keep;
+        t0 = t;
+    }
 };
 
 extern "C" size_t al_aggregate_workspace_bytes(int dtype, int64_t n, int64_t E) {
@@ -98,6 +136,7 @@ extern "C" int al_aggregate(const void* logrho, int dtype, const uint32_t* sorte
     AL_REQUIRE(n_groups_host != nullptr, AL_EINVAL, "al_aggregate: n_groups_host is NULL");
     CudaExec x;
     x.st = (cudaStream_t)stream;
+    x.prof = getenv("AL_PROFILE") != nullptr;
     AggArena ar(ws, ws_bytes);
     int rc;
     if (dtype == AL_F32)

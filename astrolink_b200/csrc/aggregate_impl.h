@@ -32,6 +32,18 @@
 #include "agg_common.h"
 
 struct uint2_agg { u32 x, y; };
+// element of a segmented sum: running sum, running count, segment-head flag
+struct SegItem { double s; u32 c; u32 f; };
+struct SegOp {
+    AGG_HD SegItem operator()(const SegItem& a, const SegItem& b) const {
+        if (b.f) return b;
+        SegItem r;
+        r.s = a.s + b.s;
+        r.c = a.c + b.c;
+        r.f = a.f;
+        return r;
+    }
+};
 
 namespace agg {
 
@@ -113,6 +125,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
 
     i64 lvl_off[MAX_LEVELS + 1], lvl_nodes[MAX_LEVELS + 1], lvl_node_off[MAX_LEVELS + 1];
 
+    x.phase("A-down");
     // ================= phase A-down: Boruvka rounds on ranks =================
     i64 N = n, m = E, M = 0, node_off = 0;
     int L = 0;
@@ -122,6 +135,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     u32* er_next = erA;
     while (m > 0) {
         if (L >= MAX_LEVELS) return -3;
+        x.phase_level("A-down", L, m, N);
         const size_t mk = ar.mark();
         u32* first = ar.get<u32>(N);
         u32* hook = ar.get<u32>(N);
@@ -137,9 +151,11 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         {
             const uint2_agg* e_ = ep;
             x.template launch<TagPickFirst>(m, AGG_LAMBDA(i64 i) {
+                // the list is in rank order, so after the first few edges of a component almost every
+                // later edge loses: a plain load (possibly stale = larger, hence safe) filters the atomics
                 uint2_agg e = e_[i];
-                agg_atomic_min(first + e.x, (u32)i);
-                agg_atomic_min(first + e.y, (u32)i);
+                if ((u32)i < first[e.x]) agg_atomic_min(first + e.x, (u32)i);
+                if ((u32)i < first[e.y]) agg_atomic_min(first + e.y, (u32)i);
             });
             x.template launch<TagHook>(N, AGG_LAMBDA(i64 s) {
                 u32 i = first[s];
@@ -228,6 +244,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     if (M != n - n_comp) return -5;
     if (M == 0) return -6;
 
+    x.phase("A-up");
     // ================= phase A-up: expand the hierarchy into the dendrogram =================
     x.fill_u32(par, NONE, M);
     x.fill_u32(child0, NONE, M);
@@ -322,6 +339,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         if ((u32)v == pk_p0node[P]) child0[P] = (u32)v; else child1[P] = (u32)v;
     });
 
+    x.phase("B-tour");
     // ================= phase B: sizes, starts, ordering, rows =================
     // ---- Euler tour over internal nodes: event 2c = enter(c), 2c+1 = exit(c)
     const i64 TL = 2 * M;
@@ -375,6 +393,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         }
         la = src;   // ranks: hops to the end of the tour
     }
+    x.phase("B-starts");
     // tour position of event e: TL-1 - rank(e); subtree(c) holds (exit-enter+1)/2 internal nodes
     u32* size_int = ar.get<u32>(M);       // leaves under internal node c
     u32* wts = ar.get<u32>(TL);           // +w at enter, -w at exit, in tour order
@@ -449,6 +468,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     }
     x.template launch<TagOrdering>(n, AGG_LAMBDA(i64 v) { ordering_out[start_leaf[v]] = (u32)v; });
 
+    x.phase("B-rows");
     // ---- range-max tree over logRho in final order
     i64 n2 = 1;
     while (n2 < n) n2 *= 2;
@@ -481,6 +501,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     u32* nv_in = ar.get<u32>(R + 1);
     u32* nv_out = ar.get<u32>(R + 1);
     u32* row_of_start = ar.get<u32>(n);
+    SegItem* items = ar.get<SegItem>(R + 1);
     double* seg_noise = ar.get<double>(R + 1);
     u32* seg_m = ar.get<u32>(R + 1);
     if (!ar.ok) return -2;
@@ -524,23 +545,35 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     if (R > 0) {
         // ---- noise correction (astrolink.py:471-485): children of a group in merge order
         x.sort_pairs_u64_u32(nk_in, nk_out, nv_in, nv_out, R, 64, ar);
-        x.template launch<TagNoise>(R, AGG_LAMBDA(i64 i) {
-            const u32 key = (u32)(nk_out[i] >> 32);
-            if (i > 0 && (u32)(nk_out[i - 1] >> 32) == key) return;    // not a segment head
-            double noise = 0.0;
-            u32 t = 0;
-            for (i64 j = i; j < R && (u32)(nk_out[j] >> 32) == key; j++, t++) {
-                const u32 r = nv_out[j];
-                if (t > 0) r_pg[r] = (T)((double)r_pg[r] - sqrt(noise / (double)t));
-                const T pl = r_pl[r];
-                noise += (double)(T)(pl * pl);
+        // exclusive per-group prefix (noise = sum of pl^2 of the earlier children, t = their count):
+        // a segmented scan over the rows in (group, merge time) order
+        x.template launch<TagMisc>(R, AGG_LAMBDA(i64 i) {
+            const bool head = i == 0 || (u32)(nk_out[i - 1] >> 32) != (u32)(nk_out[i] >> 32);
+            SegItem it;
+            if (head) { it.s = 0.0; it.c = 0; it.f = 1; }
+            else {
+                const T pl = r_pl[nv_out[i - 1]];
+                it.s = (double)(T)(pl * pl);
+                it.c = 1;
+                it.f = 0;
             }
-            seg_noise[i] = noise;
-            seg_m[i] = t;
+            items[i] = it;
+        });
+        x.segmented_inclusive_scan(items, R, ar);
+        x.template launch<TagNoise>(R, AGG_LAMBDA(i64 i) {
+            const u32 r = nv_out[i];
+            const SegItem it = items[i];
+            if (it.c > 0) r_pg[r] = (T)((double)r_pg[r] - sqrt(it.s / (double)it.c));
+            const bool last = i + 1 == R || (u32)(nk_out[i + 1] >> 32) != (u32)(nk_out[i] >> 32);
+            if (last) {
+                const T pl = r_pl[r];
+                seg_noise[i] = it.s + (double)(T)(pl * pl);
+                seg_m[i] = it.c + 1;
+            }
         });
         x.template launch<TagOwn>(R, AGG_LAMBDA(i64 i) {
             const u32 key = (u32)(nk_out[i] >> 32);
-            if (i > 0 && (u32)(nk_out[i - 1] >> 32) == key) return;
+            if (i + 1 < R && (u32)(nk_out[i + 1] >> 32) == key) return;    // totals live at the last row of a group
             const u32 own = row_of_start[key];      // the row in which this group is the smaller side
             if (own == NONE) return;                // the root group has no row
             const double corr = sqrt(seg_noise[i] / (double)seg_m[i]);
@@ -577,6 +610,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
             });
         }
     }
+    x.phase("end");
     x.sync();
     *n_groups_out = G;
     return 0;

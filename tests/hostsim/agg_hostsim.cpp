@@ -39,6 +39,12 @@ struct HostExec {
         for (i64 i = 0; i < n; i++) { k_out[i] = k_in[idx[i]]; v_out[i] = v_in[idx[i]]; }
     }
     void sync() {}
+    void phase(const char*) {}
+    void phase_level(const char*, int, i64, i64) {}
+    void segmented_inclusive_scan(SegItem* items, i64 n, AggArena&) {
+        SegOp op;
+        for (i64 i = 1; i < n; i++) items[i] = op(items[i - 1], items[i]);
+    }
 };
 
 template <typename T>
