@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libastrolink_b200.so")
+_LIB_PATH = os.environ.get("AL_LIB") or os.path.join(_HERE, "libastrolink_b200.so")   # AL_LIB: development A/B builds
 _lib = None
 
 AL_F32, AL_F64 = 0, 1

@@ -54,6 +54,19 @@ def _deps_stamp():
     return h.hexdigest()
 
 
+def build_variant(tag, defs):
+    """Development aid: builds libastrolink_b200_<tag>.so with extra -D flags (A/B tests via AL_LIB)."""
+    global OBJ, LIB, NVCC_FLAGS
+    saved = (OBJ, LIB, list(NVCC_FLAGS))
+    OBJ = os.path.join(CSRC, "build_" + tag)
+    LIB = os.path.join(HERE, f"libastrolink_b200_{tag}.so")
+    NVCC_FLAGS = NVCC_FLAGS + list(defs)
+    try:
+        return build(force=False)
+    finally:
+        OBJ, LIB, NVCC_FLAGS = saved[0], saved[1], saved[2]
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp")

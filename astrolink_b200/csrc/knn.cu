@@ -52,9 +52,9 @@ extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int
     p.stats = pairs_evaluated;
     cudaStream_t st = (cudaStream_t)stream;
     if (h.dtype == AL_F32) {
-        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride, k, h.d);
+        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride, k, h.d, h.n_levels);
         return g_knn_f32[h.d - 1](p, st);
     }
-    p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride, k, h.d);
+    p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride, k, h.d, h.n_levels);
     return g_knn_f64[h.d - 1](p, st);
 }

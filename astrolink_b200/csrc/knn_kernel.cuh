@@ -21,12 +21,33 @@
 #pragma once
 #include "index.cuh"
 
+#ifndef KNN_SPARSE_MAX
+#define KNN_SPARSE_MAX 12
+#endif
+#ifndef KNN_SPARSE4
+#define KNN_SPARSE4 0          // 1: four needy queries per sparse pass instead of two
+#endif
+#ifndef KNN_REFRESH
+#define KNN_REFRESH 0          // 1: re-test every query against the tile's box with the current k-th distances
+#endif
+#ifndef KNN_ORDER
+#define KNN_ORDER 1            // 1: visit the leaves of a wide node nearest box first
+#endif
+#ifndef KNN_QCAP
+#define KNN_QCAP 8
+#endif
+#ifndef KNN_MINBLOCKS
+#define KNN_MINBLOCKS 5
+#endif
 constexpr int WARPS = 4;             // warps (query leaves) per CTA
-constexpr int QCAP = 16;             // queue entries per lane
-constexpr int CHUNK_PB = 4;          // pair blocks (2 candidates each) between queue checks
+constexpr int QCAP = KNN_QCAP;       // queue entries per lane
+#ifndef KNN_CHUNK_PB
+#define KNN_CHUNK_PB 2
+#endif
+constexpr int CHUNK_PB = KNN_CHUNK_PB;   // pair blocks (2 candidates each) between queue checks
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int KNN_NSTATS = 8;        // counters written to the stats array (see al_knn)
-constexpr int SPARSE_MAX = 12;       // tiles needed by at most this many queries are evaluated one query at a time
+constexpr int SPARSE_MAX = KNN_SPARSE_MAX;       // tiles needed by at most this many queries are evaluated one query at a time
 static_assert(QCAP >= 4 * CHUNK_PB, "queue must absorb two chunks");
 
 struct KnnParams {
@@ -53,12 +74,12 @@ static inline int knn_qrow_elems(int d) {
     return (d + 1 + per16 - 1) / per16 * per16;
 }
 template <typename T>
-static inline int knn_warp_smem_bytes(int tile_stride, int k, int d) {
+static inline int knn_warp_smem_bytes(int tile_stride, int k, int d, int n_levels) {
     size_t b = 2 * (size_t)tile_stride;
     b += (size_t)QCAP * 32 * (sizeof(T) + 4);
     b += (size_t)k * 32 * (sizeof(T) + 4);
     b += (size_t)32 * knn_qrow_elems<T>(d) * sizeof(T);
-    b += (size_t)MAX_WIDE_LEVELS * 32 * 4;
+    b += (size_t)(n_levels + 1) * 32 * 4;
     b += (size_t)MAX_WIDE_LEVELS * (8 + 4 + 4);
     b += 16;
     return (int)al_align(b, 128);
@@ -148,61 +169,111 @@ __device__ __forceinline__ double2 lds_d2(u32 addr) {
     return v;
 }
 
+// one row of the query table (RS elements, 16-byte aligned) with 128-bit loads
+template <int RS>
+__device__ __forceinline__ void load_row(const float* row, float* out) {
+#pragma unroll
+    for (int v = 0; v < RS / 4; v++) {
+        const float4 f = reinterpret_cast<const float4*>(row)[v];
+        out[4 * v] = f.x; out[4 * v + 1] = f.y; out[4 * v + 2] = f.z; out[4 * v + 3] = f.w;
+    }
+}
+template <int RS>
+__device__ __forceinline__ void load_row(const double* row, double* out) {
+#pragma unroll
+    for (int v = 0; v < RS / 2; v++) {
+        const double2 f = reinterpret_cast<const double2*>(row)[v];
+        out[2 * v] = f.x; out[2 * v + 1] = f.y;
+    }
+}
+
 // ---------------------------------------------------------------------------
-// Per-lane top-k: a max-heap by (d2, id) in shared memory, laid out [slot][lane]
-// (bank = lane, conflict-free for any per-lane slot).  Root = current k-th (worst).
+// (distance, id) keys.  float: one 64-bit word, distance bits in the high half
+// (distances are >= 0, so unsigned order == (distance, id) lexicographic order);
+// double: a (double, u32) pair held in two arrays.
+template <typename T> struct KeyStore;
+template <> struct KeyStore<float> {
+    typedef u64 Key;
+    u64* k;
+    static constexpr int BYTES = 8;
+    __device__ __forceinline__ static Key make(float d, u32 id) { return ((u64)__float_as_uint(d) << 32) | id; }
+    __device__ __forceinline__ static bool worse(Key a, Key b) { return a > b; }
+    __device__ __forceinline__ static float dist(Key a) { return __uint_as_float((u32)(a >> 32)); }
+    __device__ __forceinline__ static u32 id(Key a) { return (u32)a; }
+    __device__ __forceinline__ Key ld(int i) const { return k[i]; }
+    __device__ __forceinline__ void st(int i, Key v) const { k[i] = v; }
+    __device__ __forceinline__ static KeyStore at(unsigned char* base, int entries) { (void)entries; KeyStore s; s.k = (u64*)base; return s; }
+};
+struct KeyD { double d; u32 id; };
+template <> struct KeyStore<double> {
+    typedef KeyD Key;
+    double* dd;
+    u32* ii;
+    static constexpr int BYTES = 12;
+    __device__ __forceinline__ static Key make(double d, u32 id) { KeyD k; k.d = d; k.id = id; return k; }
+    __device__ __forceinline__ static bool worse(Key a, Key b) { return a.d > b.d || (a.d == b.d && a.id > b.id); }
+    __device__ __forceinline__ static double dist(Key a) { return a.d; }
+    __device__ __forceinline__ static u32 id(Key a) { return a.id; }
+    __device__ __forceinline__ Key ld(int i) const { KeyD k; k.d = dd[i]; k.id = ii[i]; return k; }
+    __device__ __forceinline__ void st(int i, Key v) const { dd[i] = v.d; ii[i] = v.id; }
+    __device__ __forceinline__ static KeyStore at(unsigned char* base, int entries) {
+        KeyStore s; s.dd = (double*)base; s.ii = (u32*)(base + (size_t)entries * 8); return s;
+    }
+};
+
+// Per-lane top-k: a max-heap of keys in shared memory, laid out [slot][lane].
+// Root = current k-th (worst).  Replaces the root by `v` and restores the heap.
 template <typename T>
-__device__ __forceinline__ void heap_replace_root(T* hd, u32* hi, int K, int lane, T v, u32 id) {
+__device__ __forceinline__ void heap_replace_root(const KeyStore<T>& h, int K, int lane, typename KeyStore<T>::Key v) {
+    typedef KeyStore<T> KS;
     int pos = 0;
     for (;;) {
         const int l = 2 * pos + 1;
         if (l >= K) break;
         int c = l;
-        T cd = hd[l * 32 + lane];
-        u32 ci = hi[l * 32 + lane];
+        typename KS::Key ck = h.ld(l * 32 + lane);
         if (l + 1 < K) {
-            const T rd = hd[(l + 1) * 32 + lane];
-            const u32 ri = hi[(l + 1) * 32 + lane];
-            if (worse<T>(rd, ri, cd, ci)) { c = l + 1; cd = rd; ci = ri; }
+            const typename KS::Key rk = h.ld((l + 1) * 32 + lane);
+            if (KS::worse(rk, ck)) { c = l + 1; ck = rk; }
         }
-        if (!worse<T>(cd, ci, v, id)) break;
-        hd[pos * 32 + lane] = cd;
-        hi[pos * 32 + lane] = ci;
+        if (!KS::worse(ck, v)) break;
+        h.st(pos * 32 + lane, ck);
         pos = c;
     }
-    hd[pos * 32 + lane] = v;
-    hi[pos * 32 + lane] = id;
+    h.st(pos * 32 + lane, v);
 }
 
 template <typename T, int D>
 struct WarpState {
     T q[D];
-    T worst;        // root of the heap for real queries, -1 for padding lanes
+    T worst;        // distance of the heap root for real queries, -1 for padding lanes
     T bound;        // warp max of worst
+    typename KeyStore<T>::Key root;   // cached heap root
     int cnt;        // queue fill
     bool active;
     u32 n_push, n_insert;   // statistics
 };
 
 template <typename T, int D>
-__device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const T* qd, const u32* qi, T* hd, u32* hi, T* qworst, int K,
+__device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<T>& qk, const KeyStore<T>& hk, T* qworst, int K,
                                              int lane, u32& n_flush, u32& n_iter) {
+    typedef KeyStore<T> KS;
     const int maxc = __reduce_max_sync(FULL, s.cnt);
     n_flush++;
     n_iter += maxc;
 #pragma unroll 1
     for (int t = 0; t < maxc; t++) {
         if (t < s.cnt) {
-            const T v = qd[t * 32 + lane];
-            const u32 id = qi[t * 32 + lane];
-            if (worse<T>(hd[lane], hi[lane], v, id)) {
-                heap_replace_root<T>(hd, hi, K, lane, v, id);
+            const typename KS::Key v = qk.ld(t * 32 + lane);
+            if (KS::worse(s.root, v)) {
+                heap_replace_root<T>(hk, K, lane, v);
+                s.root = hk.ld(lane);
                 s.n_insert++;
             }
         }
     }
     s.cnt = 0;
-    if (s.active) s.worst = hd[lane];
+    if (s.active) s.worst = KS::dist(s.root);
     qworst[0] = s.worst;            // this lane's row of the query table
     __syncwarp();
     s.bound = warp_max_t<T>(s.worst);
@@ -253,8 +324,33 @@ __device__ __forceinline__ void chunk_dist(const double* q, u32 coords, int pair
     }
 }
 
+// distance from query rows ra / rb (query table) to this lane's candidate cc: two queries per pass
+template <int D>
+__device__ __forceinline__ void pair_dist(const float* ra, const float* rb, const float* cc, float& va, float& vb) {
+    u64 acc = 0ull;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const u64 df = sub2(pack2(ra[j], rb[j]), pack2(cc[j], cc[j]));
+        acc = fma2(df, df, acc);
+    }
+    unpack2(acc, va, vb);
+}
+template <int D>
+__device__ __forceinline__ void pair_dist(const double* ra, const double* rb, const double* cc, double& va, double& vb) {
+    va = 0.0;
+    vb = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const double da = ra[j] - cc[j], db = rb[j] - cc[j];
+        va = __fma_rn(da, da, va);
+        vb = __fma_rn(db, db, vb);
+    }
+}
+
 template <typename T, int D>
-__global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const KnnParams p) {
+    typedef KeyStore<T> KS;
+    typedef typename KS::Key Key;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const i64 ql = p.leaf_begin + (i64)blockIdx.x * WARPS + wib;
@@ -265,18 +361,19 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
     constexpr int PER16 = 16 / (int)sizeof(T);
     constexpr int RS = (D + 1 + PER16 - 1) / PER16 * PER16;   // query-table row stride (elements)
     const u32 wo = (u32)wib * (u32)p.warp_smem;
-    const u32 o_q = 2u * (u32)p.tile_stride;
-    T* qd = (T*)(smem + wo + o_q);                          // [QCAP][32]
-    u32* qi = (u32*)(qd + QCAP * 32);                       // [QCAP][32]
-    T* hd = (T*)(qi + QCAP * 32);                           // [K][32] heap distances
-    u32* hi = (u32*)(hd + K * 32);                          // [K][32] heap ids
-    T* qtab = (T*)(hi + K * 32);                            // [32][RS]: query coordinates, k-th distance
-    u32* sneed = (u32*)(qtab + 32 * RS);                    // [MAX_WIDE_LEVELS][32] per-child query masks
-    i64* snode = (i64*)(sneed + MAX_WIDE_LEVELS * 32);      // [MAX_WIDE_LEVELS]
+    unsigned char* wbase = smem + wo;
+    unsigned char* o = wbase + 2u * (u32)p.tile_stride;
+    const KS qk = KS::at(o, QCAP * 32);                     // [QCAP][32] queue of keys
+    o += (size_t)QCAP * 32 * KS::BYTES;
+    const KS hk = KS::at(o, K * 32);                        // [K][32] heap of keys
+    o += (size_t)K * 32 * KS::BYTES;
+    T* qtab = (T*)o;                                        // [32][RS]: query coordinates, k-th distance
+    u32* sneed = (u32*)(qtab + 32 * RS);                    // [n_levels + 1][32] per-child query masks
+    i64* snode = (i64*)(sneed + (p.n_levels + 1) * 32);     // [MAX_WIDE_LEVELS]
     u32* smask = (u32*)(snode + MAX_WIDE_LEVELS);           // [MAX_WIDE_LEVELS]
     int* slevel = (int*)(smask + MAX_WIDE_LEVELS);          // [MAX_WIDE_LEVELS]
     u64* bars = (u64*)(slevel + MAX_WIDE_LEVELS);           // [2]
-    const u32 tile_sa = smem_u32(smem + wo);                // shared address of tile buffer 0
+    const u32 tile_sa = smem_u32(wbase);                    // shared address of tile buffer 0
     T* qworst = qtab + lane * RS + D;
 
     if (lane == 0) {
@@ -284,8 +381,9 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const Key kinf = KS::make(inf_t<T>(), 0xffffffffu);
 #pragma unroll 1
-    for (int m = 0; m < K; m++) { hd[m * 32 + lane] = inf_t<T>(); hi[m * 32 + lane] = 0xffffffffu; }
+    for (int m = 0; m < K; m++) hk.st(m * 32 + lane, kinf);
 #pragma unroll
     for (int j = 0; j < RS; j++) qtab[lane * RS + j] = j == D ? (T)-1 : (T)0;
     __syncwarp();
@@ -295,6 +393,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
     s.active = false;
     s.worst = (T)-1;
     s.bound = inf_t<T>();
+    s.root = kinf;
     s.n_push = 0;
     s.n_insert = 0;
     u32 n_flush = 0, n_iter = 0, n_loaded = 0, n_eval = 0, n_needy = 0, n_slow = 0;
@@ -316,6 +415,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
     // Open a wide node: lane j takes child j (level `hc`), tests box-to-box against the warp bound, then
     // for every query in `qmask` the distance from the query to the child's box against the query's own
     // k-th distance.  Returns the children some query needs; per-child query masks go to need_out[lane].
+    u32 top_dist = 0xffffffffu;     // this lane's child-box distance (float bits) of the most recent open
     auto open_node = [&](int hc, i64 node, i64 excl, u32 qmask, u32* need_out) -> u32 {
         const i64 cnt = p.count[hc];
         const i64 c = node * FANOUT + lane;
@@ -341,12 +441,12 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             while (m) {
                 const int q = __ffs(m) - 1;
                 m &= m - 1;
-                const T* row = qtab + q * RS;
+                T row[RS];
+                load_row<RS>(qtab + q * RS, row);
                 T pd = (T)0;
 #pragma unroll
                 for (int j = 0; j < D; j++) {
-                    const T x = row[j];
-                    T a = blo[j] - x, b = x - bhi[j];
+                    T a = blo[j] - row[j], b = row[j] - bhi[j];
                     T g = a > b ? a : b;
                     g = g > (T)0 ? g : (T)0;
                     pd = fma_t<T>(g, g, pd);
@@ -355,12 +455,17 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             }
         }
         need_out[lane] = mask;
+        top_dist = mask != 0 ? __float_as_uint((float)acc) : 0xffffffffu;   // order only; float precision is enough
         return __ballot_sync(FULL, mask != 0);
     };
 
-    // ---- traversal state: ancestors of the own leaf, bottom-up; a small stack for descents
+    // ---- traversal state: ancestors of the own leaf, bottom-up; a small stack for descents.
+    // The top entry (children mask, node, level) lives in registers; lower entries in shared memory.
     int anc = 0;    // 0: own leaf not yet emitted; g >= 1: next ancestor level to open
-    int sp = 0;
+    int sp = 0;     // entries on the stack, including the register-resident top
+    u32 t_mask = 0;
+    i64 t_node = 0;
+    int t_h = 0;
     u32 cand_need = FULL;
     auto next_candidate = [&]() -> i64 {
         if (anc == 0) { anc = 1; cand_need = FULL; return ql; }
@@ -368,34 +473,57 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             if (sp == 0) {
                 if (anc > p.n_levels) return -1;
                 // open the children of the level-`anc` ancestor, except the branch already done
-                if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qd, qi, hd, hi, qworst, K, lane, n_flush, n_iter);
+                if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
                 const i64 node = ql >> (5 * anc), excl = ql >> (5 * (anc - 1));
-                const u32 m = open_node(anc - 1, node, excl, FULL, sneed);
-                if (lane == 0) { smask[0] = m; snode[0] = node; slevel[0] = anc; }
+                t_mask = open_node(anc - 1, node, excl, FULL, sneed);
+                t_node = node;
+                t_h = anc;
                 __syncwarp();
                 sp = 1;
                 anc++;
                 continue;
             }
-            const int top = sp - 1;
-            u32 m = smask[top];
-            if (m == 0) { sp--; continue; }
-            const int h = slevel[top];
-            const i64 node = snode[top];
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const u32 need = sneed[top * 32 + bit];
+            if (t_mask == 0) {
+                sp--;
+                if (sp > 0) { t_mask = smask[sp - 1]; t_node = snode[sp - 1]; t_h = slevel[sp - 1]; }
+                continue;
+            }
+            int bit;
+            if (KNN_ORDER && t_h == 1) {
+                // leaves: nearest box first, so the k-th distances tighten as early as possible
+                const u32 key = ((t_mask >> lane) & 1u) ? top_dist : 0xffffffffu;
+                const u32 mn = __reduce_min_sync(FULL, key);
+                bit = __ffs(__ballot_sync(FULL, key == mn)) - 1;
+            } else {
+                bit = __ffs(t_mask) - 1;
+            }
+            t_mask &= ~(1u << bit);
+            const u32 need = sneed[(sp - 1) * 32 + bit];
+            const i64 c = t_node * FANOUT + bit;
+            if (t_h == 1) { cand_need = need; return c; }
+            // descend: save the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
+            if (lane == 0) { smask[sp - 1] = t_mask; snode[sp - 1] = t_node; slevel[sp - 1] = t_h; }
+            t_mask = open_node(t_h - 2, c, -1, need, sneed + sp * 32);
+            t_node = c;
+            t_h = t_h - 1;
             __syncwarp();
-            if (lane == 0) smask[top] = m;
-            __syncwarp();
-            const i64 c = node * FANOUT + bit;
-            if (h == 1) { cand_need = need; return c; }
-            // descend: open the children of node c (a level h-1 node) for the queries that need it
-            {
-                const u32 mm = open_node(h - 2, c, -1, need, sneed + sp * 32);
-                if (lane == 0) { smask[sp] = mm; snode[sp] = c; slevel[sp] = h - 1; }
-                __syncwarp();
-                sp++;
+            sp++;
+        }
+    };
+
+    // hits of one needy query (sparse path): owner lane `q` queues every candidate flagged in `hm`
+    auto emit_hits = [&](u32 hm, T v, u32 cid, int q) {
+#pragma unroll 1
+        while (hm) {
+            const int b = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const T vv = __shfl_sync(FULL, v, b);
+            const u32 ii = __shfl_sync(FULL, cid, b);
+            if (__shfl_sync(FULL, s.cnt, q) >= QCAP) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
+            if (lane == q) {
+                qk.st(s.cnt * 32 + lane, KS::make(vv, ii));
+                s.cnt++;
+                s.n_push++;
             }
         }
     };
@@ -413,7 +541,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             __syncwarp();       // every lane is done reading buffer bi
             if (lane == 0) {
                 mbar_expect_tx(&bars[bi], (u32)p.tile_stride);
-                tma_load_1d(smem + wo + (u32)bi * (u32)p.tile_stride, p.tiles + cand * (i64)p.tile_stride, (u32)p.tile_stride,
+                tma_load_1d(wbase + (u32)bi * (u32)p.tile_stride, p.tiles + cand * (i64)p.tile_stride, (u32)p.tile_stride,
                             &bars[bi]);
             }
             n_loaded++;
@@ -422,7 +550,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             const int bw = bi ^ 1;
             while (!mbar_try_wait(&bars[bw], (phase >> bw) & 1u)) {}
             phase ^= (1u << bw);
-            const unsigned char* tile = smem + wo + (u32)bw * (u32)p.tile_stride;
+            const unsigned char* tile = wbase + (u32)bw * (u32)p.tile_stride;
             const T* hdr = (const T*)tile;
             const T* tcoord = (const T*)(tile + p.tile_hdr_bytes);
             const u32* ids = (const u32*)(tile + p.tile_ids_off);
@@ -440,7 +568,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
                 qworst[0] = s.worst;
                 __syncwarp();
                 need = FULL;
-            } else {
+            } else if (KNN_REFRESH) {
                 // refresh the need mask with the current k-th distances
                 T acc = (T)0;
 #pragma unroll
@@ -452,6 +580,11 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
                 }
                 need = __ballot_sync(FULL, acc <= s.worst) & pending_need;
                 n_needy += __popc(need);
+                n_slow += __popc(pending_need);
+            } else {
+                need = pending_need;
+                n_needy += __popc(need);
+                n_slow += __popc(need);
             }
             const int n_need = __popc(need);
             if (n_need > SPARSE_MAX) {
@@ -460,8 +593,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
                 n_pairs += (unsigned long long)LEAF * 32;
                 const u32 coords = tile_sa + (u32)bw * (u32)p.tile_stride + (u32)p.tile_hdr_bytes;
                 // each chunk may push 2*CHUNK_PB entries per lane; the sparse path can leave queues fuller than that allows
-                if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB))
-                    flush_queues<T, D>(s, qd, qi, hd, hi, qworst, K, lane, n_flush, n_iter);
+                if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
 #pragma unroll 1
                 for (int pb0 = 0; pb0 < LEAF / 2; pb0 += CHUNK_PB) {
                     T v[2 * CHUNK_PB];
@@ -470,22 +602,20 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
 #pragma unroll
                     for (int e = 1; e < 2 * CHUNK_PB; e++) mn = v[e] < mn ? v[e] : mn;
                     if (__any_sync(FULL, mn <= s.worst)) {
-                        n_slow++;
 #pragma unroll
                         for (int e = 0; e < 2 * CHUNK_PB; e++) {
                             if (v[e] <= s.worst) {
-                                qd[s.cnt * 32 + lane] = v[e];
-                                qi[s.cnt * 32 + lane] = ids[2 * pb0 + e];
+                                qk.st(s.cnt * 32 + lane, KS::make(v[e], ids[2 * pb0 + e]));
                                 s.cnt++;
                                 s.n_push++;
                             }
                         }
                         if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB))
-                            flush_queues<T, D>(s, qd, qi, hd, hi, qworst, K, lane, n_flush, n_iter);
+                            flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
                     }
                 }
             } else if (n_need > 0) {
-                // ---- sparse: one needy query at a time, lane l evaluates candidate l
+                // ---- sparse: two needy queries per pass, lane l evaluates candidate l for both
                 n_eval++;
                 n_pairs += (unsigned long long)LEAF * n_need;
                 T cc[D];
@@ -493,34 +623,55 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
                 for (int j = 0; j < D; j++) cc[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
                 const u32 cid = ids[lane];
                 u32 m = need;
+#if KNN_SPARSE4
 #pragma unroll 1
                 while (m) {
-                    const int q = __ffs(m) - 1;
-                    m &= m - 1;
-                    const T* row = qtab + q * RS;
-                    T v = (T)0;
+                    // up to four needy queries per pass: two packed pairs, independent dependency chains
+                    int qv[4];
+                    bool on[4];
 #pragma unroll
-                    for (int j = 0; j < D; j++) {
-                        const T df = row[j] - cc[j];
-                        v = fma_t<T>(df, df, v);
+                    for (int e = 0; e < 4; e++) {
+                        on[e] = m != 0;
+                        qv[e] = on[e] ? __ffs(m) - 1 : qv[0];
+                        m &= m - 1;
                     }
-                    u32 hm = __ballot_sync(FULL, v <= row[D]);
-#pragma unroll 1
-                    while (hm) {
-                        const int b = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const T vv = __shfl_sync(FULL, v, b);
-                        const u32 ii = __shfl_sync(FULL, cid, b);
-                        if (__shfl_sync(FULL, s.cnt, q) >= QCAP)
-                            flush_queues<T, D>(s, qd, qi, hd, hi, qworst, K, lane, n_flush, n_iter);
-                        if (lane == q) {
-                            qd[s.cnt * 32 + lane] = vv;
-                            qi[s.cnt * 32 + lane] = ii;
-                            s.cnt++;
-                            s.n_push++;
-                        }
-                    }
+                    T r0[RS], r1[RS], r2[RS], r3[RS];
+                    load_row<RS>(qtab + qv[0] * RS, r0);
+                    load_row<RS>(qtab + qv[1] * RS, r1);
+                    load_row<RS>(qtab + qv[2] * RS, r2);
+                    load_row<RS>(qtab + qv[3] * RS, r3);
+                    T v0, v1, v2, v3;
+                    pair_dist<D>(r0, r1, cc, v0, v1);
+                    pair_dist<D>(r2, r3, cc, v2, v3);
+                    const u32 h0 = __ballot_sync(FULL, v0 <= r0[D]);
+                    const u32 h1 = on[1] ? __ballot_sync(FULL, v1 <= r1[D]) : 0u;
+                    const u32 h2 = on[2] ? __ballot_sync(FULL, v2 <= r2[D]) : 0u;
+                    const u32 h3 = on[3] ? __ballot_sync(FULL, v3 <= r3[D]) : 0u;
+                    if (h0) emit_hits(h0, v0, cid, qv[0]);
+                    if (h1) emit_hits(h1, v1, cid, qv[1]);
+                    if (h2) emit_hits(h2, v2, cid, qv[2]);
+                    if (h3) emit_hits(h3, v3, cid, qv[3]);
                 }
+#else
+#pragma unroll 1
+                while (m) {
+                    // two needy queries per pass (one packed f32x2 chain)
+                    const int qa = __ffs(m) - 1;
+                    m &= m - 1;
+                    const bool two = m != 0;
+                    const int qb = two ? __ffs(m) - 1 : qa;
+                    m &= m - 1;
+                    T ra[RS], rb[RS];
+                    load_row<RS>(qtab + qa * RS, ra);
+                    load_row<RS>(qtab + qb * RS, rb);
+                    T va, vb;
+                    pair_dist<D>(ra, rb, cc, va, vb);
+                    const u32 ha = __ballot_sync(FULL, va <= ra[D]);
+                    const u32 hb = two ? __ballot_sync(FULL, vb <= rb[D]) : 0u;
+                    if (ha) emit_hits(ha, va, cid, qa);
+                    if (hb) emit_hits(hb, vb, cid, qb);
+                }
+#endif
             }
         }
         if (!lookahead) { pending = -1; continue; }
@@ -529,16 +680,14 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
         pending_need = cneed;
         bi ^= 1;
     }
-    if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qd, qi, hd, hi, qworst, K, lane, n_flush, n_iter);
+    if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
 
     // ---- heap -> ascending order in place (heapsort), then write the rows
 #pragma unroll 1
     for (int m = K - 1; m >= 1; m--) {
-        const T td = hd[m * 32 + lane];
-        const u32 ti = hi[m * 32 + lane];
-        hd[m * 32 + lane] = hd[lane];
-        hi[m * 32 + lane] = hi[lane];
-        heap_replace_root<T>(hd, hi, m, lane, td, ti);
+        const Key t = hk.ld(m * 32 + lane);
+        hk.st(m * 32 + lane, hk.ld(lane));
+        heap_replace_root<T>(hk, m, lane, t);
     }
     const i64 pos_row = (ql - p.leaf_begin) * LEAF + lane;
     if (s.active) {
@@ -546,7 +695,11 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
         u32* io = p.idx_out + row * K;
         T* dd = (T*)p.d2_out + row * K;
 #pragma unroll 1
-        for (int m = 0; m < K; m++) { io[m] = hi[m * 32 + lane]; dd[m] = hd[m * 32 + lane]; }
+        for (int m = 0; m < K; m++) {
+            const Key t = hk.ld(m * 32 + lane);
+            io[m] = KS::id(t);
+            dd[m] = KS::dist(t);
+        }
     } else if (p.row_order == 1) {
 #pragma unroll 1
         for (int m = 0; m < K; m++) { p.idx_out[pos_row * K + m] = 0xffffffffu; ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>(); }
@@ -557,11 +710,11 @@ __global__ void __launch_bounds__(WARPS * 32, 4) knn_kernel(const KnnParams p) {
             atomicAdd(p.stats + 0, n_pairs);                                         // (query, candidate) pairs evaluated
             atomicAdd(p.stats + 1, (unsigned long long)n_loaded);                       // tiles fetched by TMA
             atomicAdd(p.stats + 2, (unsigned long long)n_eval);                         // tiles evaluated
-            atomicAdd(p.stats + 3, (unsigned long long)n_needy);                        // lanes that needed an evaluated/skipped tile
+            atomicAdd(p.stats + 3, (unsigned long long)n_needy);                        // lanes that needed a fetched tile
             atomicAdd(p.stats + 4, (unsigned long long)pushes);                         // queue pushes
             atomicAdd(p.stats + 5, (unsigned long long)inserts);                        // heap insertions
-            atomicAdd(p.stats + 6, (unsigned long long)n_iter);                         // flush iterations (n_flush in high half)
-            atomicAdd(p.stats + 7, (unsigned long long)n_slow);                         // chunks that took the push path
+            atomicAdd(p.stats + 6, (unsigned long long)n_iter);                         // merge iterations
+            atomicAdd(p.stats + 7, (unsigned long long)n_slow);                         // lanes needing a tile before the refresh
         }
         (void)n_flush;
     }

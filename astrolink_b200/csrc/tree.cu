@@ -120,7 +120,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
                                                              const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
                                                              const u32* __restrict__ bbox_lo, const u32* __restrict__ bbox_hi,
-                                                             u64* keys, i64 n, int d) {
+                                                             u32* keys, i64 n, int d, int cbits) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     i64 leaf = p / LEAF;
@@ -128,21 +128,25 @@ __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict
     u32 low;
     if (nodeB[leaf] - a > 1) {
         int dim = 0;
-        u32 best = 0;
+        float best = -1.f, blo = 0.f, bext = 0.f;
+        auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
         for (int j = 0; j < d; j++) {
-            // ordered-uint difference is monotone in the float extent for finite values of equal sign
-            // pattern; use the float extent itself for a faithful argmax
-            u32 lo = bbox_lo[(i64)a * d + j], hi = bbox_hi[(i64)a * d + j];
-            auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
-            float ext = dec(hi) - dec(lo);
-            u32 e = __float_as_uint(ext > 0.f ? ext : 0.f);
-            if (j == 0 || e > best) { best = e; dim = j; }
+            const float lo = dec(bbox_lo[(i64)a * d + j]), hi = dec(bbox_hi[(i64)a * d + j]);
+            float ext = hi - lo;
+            ext = ext > 0.f ? ext : 0.f;
+            if (ext > best) { best = ext; dim = j; blo = lo; bext = ext; }
         }
-        low = f32_to_ordered((float)P[(i64)perm[p] * d + dim]);
+        // the coordinate along the widest axis, quantised to cbits within the node's box: the tree only
+        // needs a balanced partition of reasonable quality, so ties inside one quantum may fall either side
+        const float x = (float)P[(i64)perm[p] * d + dim];
+        const float top = (float)((1u << cbits) - 1u);
+        float qf = bext > 0.f ? (x - blo) / bext * top : 0.f;
+        qf = qf < 0.f ? 0.f : (qf > top ? top : qf);
+        low = (u32)qf;
     } else {
         low = (u32)(p - leaf * LEAF);
     }
-    keys[p] = ((u64)a << 32) | low;
+    keys[p] = (a << cbits) | low;
 }
 
 __global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves) {
@@ -215,7 +219,7 @@ __global__ void tree_build_level_kernel(const T* __restrict__ clo, const T* __re
 
 // ---------------------------------------------------------------------------
 struct BuildWs {
-    u64 *keys0, *keys1;
+    u32 *keys0, *keys1;
     u32 *vals1;
     u32 *nodeA, *nodeB;
     u32 *bbox_lo, *bbox_hi;
@@ -225,8 +229,8 @@ struct BuildWs {
 
 static size_t sort_temp_bytes(i64 n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const u64*)nullptr, (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr,
-                                    (i64)n, 0, 64, (cudaStream_t)0);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
+                                    (i64)n, 0, 32, (cudaStream_t)0);
     return bytes;
 }
 
@@ -244,8 +248,8 @@ extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
     (void)dtype;
     i64 n_leaves = (n + LEAF - 1) / LEAF;
     ArenaSizer s;
-    s.add<u64>(n);
-    s.add<u64>(n);
+    s.add<u32>(n);
+    s.add<u32>(n);
     s.add<u32>(n);
     s.add<u32>(n_leaves);
     s.add<u32>(n_leaves);
@@ -261,8 +265,8 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     const int d = h.d;
     Arena ar(ws, ws_bytes);
     BuildWs w;
-    w.keys0 = ar.get<u64>(n);
-    w.keys1 = ar.get<u64>(n);
+    w.keys0 = ar.get<u32>(n);
+    w.keys1 = ar.get<u32>(n);
     w.vals1 = ar.get<u32>(n);
     w.nodeA = ar.get<u32>(n_leaves);
     w.nodeB = ar.get<u32>(n_leaves);
@@ -275,7 +279,7 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     char* base = (char*)index;
     u32* perm = (u32*)(base + h.perm_off);
     u32* vals[2] = {perm, w.vals1};
-    u64* keys[2] = {w.keys0, w.keys1};
+    u32* keys[2] = {w.keys0, w.keys1};
     int cur = 0;
 
     tree_init_kernel<<<al_grid(n, 256), 256, 0, st>>>(perm, w.nodeA, w.nodeB, n, n_leaves);
@@ -284,6 +288,9 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     int rounds = tree_depth(n_leaves);
     int node_bits = 1;
     while (((i64)1 << node_bits) < n_leaves) node_bits++;
+    int cbits = 32 - node_bits;          // quantised-coordinate bits of the 32-bit sort key
+    if (cbits > 16) cbits = 16;
+    AL_REQUIRE(cbits >= 5, AL_EINVAL, "al_index_build: too many leaves for 32-bit sort keys");
     for (int r = 0; r < rounds; r++) {
         AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
         AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
@@ -292,11 +299,11 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
             P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, n, n_leaves, d);
         AL_CHECK_LAUNCH();
         tree_make_keys_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, keys[cur], n, d);
+            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, keys[cur], n, d, cbits);
         AL_CHECK_LAUNCH();
         size_t tb = w.cub_bytes;
         AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
-                                                32 + node_bits, st));
+                                                cbits + node_bits, st));
         cur ^= 1;
         tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves);
         AL_CHECK_LAUNCH();

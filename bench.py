@@ -73,7 +73,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -286,6 +286,7 @@ def run_b200(args):
                      "peak_source": "FP32 FMA issue rate measured in this run (al_fp32_peak_tflops); MEASURED_PEAKS.json has no FP32 figure",
                      "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak"},
         "stage_ms": stages_out,
+        "host_timers_ms": {k: round(1e3 * getattr(c, k), 2) for k in ("_transformTime", "_logRhoTime", "_aggregateTime", "_regrTime", "_rejTime", "_totalTime")},
         "hbm_passes": others,
     }
     if world == 1 and not args.no_cpu_baseline:
