@@ -44,6 +44,7 @@ _SIGS = {
     "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
     "al_fp32_peak_tflops": (_int, [_vp, _vp]),
     "al_launch_count": (_i64, []),
+    "al_significance": (_int, [_vp, _int, _i64, _c.c_double, _c.c_double, _vp, _vp]),
 }
 
 
@@ -241,6 +242,15 @@ def fp32_peak_tflops():
     v = ctypes.c_double(0.0)
     _check(L.al_fp32_peak_tflops(ctypes.byref(v), _stream()), "al_fp32_peak_tflops")
     return float(v.value)
+
+
+def significance(prom, a, b):
+    """f1: norm.isf(beta.sf(prom, a, b)) element-wise -> float64 tensor of prom's shape."""
+    L = lib()
+    assert prom.is_contiguous()
+    out = torch.empty(prom.shape, dtype=torch.float64, device=prom.device)
+    _check(L.al_significance(_ptr(prom), _dt(prom), prom.numel(), float(a), float(b), _ptr(out), _stream()), "al_significance")
+    return out
 
 
 def launch_count():

@@ -397,7 +397,8 @@ class AstroLink:
         self.pFit, ok = stats.fit_prominence_model(prom[:, 1])
         if not ok:
             self._printFunction('[Warning] Prominence model fitting failed to converge!', returnLine=False, urgent=True)
-        self.groups_sigs = stats.significances_of(prom, self.pFit)
+        with torch.cuda.device(self._device):
+            self.groups_sigs = nat.significance(self._dev("prominences"), self.pFit[0], self.pFit[1]).cpu().numpy()
         self._regrTime = time.perf_counter() - start
 
     def extract_clusters(self):

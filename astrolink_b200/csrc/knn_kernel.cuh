@@ -33,6 +33,9 @@
 #ifndef KNN_ORDER
 #define KNN_ORDER 1            // 1: visit the leaves of a wide node nearest box first
 #endif
+#ifndef KNN_STATS
+#define KNN_STATS 0            // 1: maintain the diagnostic counters [3..7] of the stats array
+#endif
 #ifndef KNN_QCAP
 #define KNN_QCAP 8
 #endif
@@ -259,8 +262,7 @@ __device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<
                                              int lane, u32& n_flush, u32& n_iter) {
     typedef KeyStore<T> KS;
     const int maxc = __reduce_max_sync(FULL, s.cnt);
-    n_flush++;
-    n_iter += maxc;
+    if (KNN_STATS) { n_flush++; n_iter += maxc; }
 #pragma unroll 1
     for (int t = 0; t < maxc; t++) {
         if (t < s.cnt) {
@@ -268,7 +270,7 @@ __device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<
             if (KS::worse(s.root, v)) {
                 heap_replace_root<T>(hk, K, lane, v);
                 s.root = hk.ld(lane);
-                s.n_insert++;
+                if (KNN_STATS) s.n_insert++;
             }
         }
     }
@@ -327,13 +329,16 @@ __device__ __forceinline__ void chunk_dist(const double* q, u32 coords, int pair
 // distance from query rows ra / rb (query table) to this lane's candidate cc: two queries per pass
 template <int D>
 __device__ __forceinline__ void pair_dist(const float* ra, const float* rb, const float* cc, float& va, float& vb) {
-    u64 acc = 0ull;
+    // two independent scalar chains: the FP32 pipe is not the limit here, issue slots are, and packing
+    // two query rows into f32x2 operands costs more register moves than the packed math saves
+    va = 0.f;
+    vb = 0.f;
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const u64 df = sub2(pack2(ra[j], rb[j]), pack2(cc[j], cc[j]));
-        acc = fma2(df, df, acc);
+        const float da = ra[j] - cc[j], db = rb[j] - cc[j];
+        va = __fmaf_rn(da, da, va);
+        vb = __fmaf_rn(db, db, vb);
     }
-    unpack2(acc, va, vb);
 }
 template <int D>
 __device__ __forceinline__ void pair_dist(const double* ra, const double* rb, const double* cc, double& va, double& vb) {
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             if (lane == q) {
                 qk.st(s.cnt * 32 + lane, KS::make(vv, ii));
                 s.cnt++;
-                s.n_push++;
+                if (KNN_STATS) s.n_push++;
             }
         }
     };
@@ -583,8 +588,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 n_slow += __popc(pending_need);
             } else {
                 need = pending_need;
-                n_needy += __popc(need);
-                n_slow += __popc(need);
+                if (KNN_STATS) { n_needy += __popc(need); n_slow += __popc(need); }
             }
             const int n_need = __popc(need);
             if (n_need > SPARSE_MAX) {
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                             if (v[e] <= s.worst) {
                                 qk.st(s.cnt * 32 + lane, KS::make(v[e], ids[2 * pb0 + e]));
                                 s.cnt++;
-                                s.n_push++;
+                                if (KNN_STATS) s.n_push++;
                             }
                         }
                         if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB))

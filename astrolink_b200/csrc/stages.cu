@@ -426,3 +426,69 @@ extern "C" int al_fp32_peak_tflops(double* tflops_host, void* stream) {
     *tflops_host = best;
     return AL_OK;
 }
+
+// ---------------------------------------------------------------------------
+// f1: groups_sigs = norm.isf(beta.sf(prominences, a, b))  (astrolink.py:858)
+// Element-wise, float64: the survival function of Beta(a, b) by the continued
+// fraction of the regularised incomplete beta function (modified Lentz), taken
+// on the side that keeps the small tail accurate, then the inverse normal
+// survival function.  The Beta-model FIT stays on the host (north-star item 5).
+// ---------------------------------------------------------------------------
+__device__ static double beta_cf(double a, double b, double x) {
+    const double tiny = 1e-300, eps = 1e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 1000; m++) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+
+__device__ static double beta_sf(double x, double a, double b, double lbeta) {
+    if (!(x > 0.0)) return x != x ? x : 1.0;
+    if (x >= 1.0) return 0.0;
+    const double front = exp(a * log(x) + b * log1p(-x) - lbeta);
+    if (x < (a + 1.0) / (a + b + 2.0)) return 1.0 - front * beta_cf(a, b, x) / a;   // cdf is the small side
+    return front * beta_cf(b, a, 1.0 - x) / b;                                       // sf is the small side
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) significance_kernel(const T* __restrict__ prom, i64 count, double a, double b, double lbeta,
+                                                           double* __restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double sf = beta_sf((double)prom[i], a, b, lbeta);
+    out[i] = -normcdfinv(sf);    // norm.isf(p) = -ndtri(p)
+}
+
+extern "C" int al_significance(const void* prominences, int dtype, int64_t count, double a, double b, double* sig_out, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_significance: bad dtype");
+    AL_REQUIRE(count >= 0 && a > 0.0 && b > 0.0, AL_EINVAL, "al_significance: bad arguments");
+    if (count == 0) return AL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+    unsigned grid = (unsigned)((count + 255) / 256);
+    if (dtype == AL_F32) significance_kernel<float><<<grid, 256, 0, st>>>((const float*)prominences, count, a, b, lbeta, sig_out);
+    else significance_kernel<double><<<grid, 256, 0, st>>>((const double*)prominences, count, a, b, lbeta, sig_out);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}

