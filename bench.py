@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", help="C4 (default, 10M x 6D) or C2/C3 or n=<points> for a reduced halo")
-    ap.add_argument("--cpu-sample", type=int, default=400000, help="points in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=3000000, help="points in the cpu_baseline sample (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -61,53 +61,93 @@ def make_workload(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks and throttle reasons sampled DURING the timed region.  Uses NVML in-process
+    (the library behind nvidia-smi): an `nvidia-smi -lms` child was measured to stall the GPU
+    for ~50 ms per sample on this driver, which is larger than a third of one step.  Falls
+    back to the recipe's `nvidia-smi --query-gpu ... -lms` line if NVML cannot be loaded."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index, period_s=0.05):
         self.gpu = gpu_index
+        self.period = period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.mode = None
+        self.proc = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                return self.gpu
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.mode = "nvml"
+            self.th = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "1000",
+                                          "-i", str(self._visible_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
+            self.th = threading.Thread(target=self._loop_smi, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.mode = None
 
-    def _read(self):
+    def _loop_nvml(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _loop_smi(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                self.sm.append(float(f[0]))
+                self.mx.append(float(f[1]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [s for s in sm if s > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        if self.proc is not None:
+            self.proc.terminate()
+        self.th.join(timeout=2)
+        busy = [s for s in self.sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.mode}
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -134,7 +174,7 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     P, kwargs, desc = make_workload(args.workload)
-    n_s = min(args.cpu_sample * 2, P.shape[0])
+    n_s = min(args.cpu_sample, P.shape[0])
     sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_hot_path_seconds(sample[: max(20000, n_s // 20)], kwargs)
@@ -213,6 +253,7 @@ def run_b200(args):
         marks[0].record()
         last = None
         for i in range(steps):
+            last = None                       # release the previous step's buffers first (as a caller re-running would)
             last = one_run(resident)
             marks[i + 1].record()
         e1.record()
@@ -232,12 +273,15 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms_value, c, launches, steps_value = timed(True, args.steps)
-    ms_e2e, c2, _, steps_e2e = timed(False, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- roofline of the dominant kernel (kNN), from the last timed resident run
+    # ---- roofline inputs of the dominant kernel (kNN), from the last timed resident run
     stage = c.stage_ms()
     pairs = int(c._knn_pairs[0].item())
+    host_timers = {k: round(1e3 * getattr(c, k), 2) for k in ("_transformTime", "_logRhoTime", "_aggregateTime", "_regrTime", "_rejTime", "_totalTime")}
+    K, L = c.k_den, c.k_link
+    n_groups, n_clusters = (int(c.groups.shape[0]), int(c.clusters.shape[0])) if rank == 0 else (0, 0)
+    c = None                                  # release its buffers before the e2e series
+    ms_e2e, c2, _, steps_e2e = timed(False, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     if D is not None:
         import torch.distributed as td
         t = torch.tensor([float(pairs), stage["knn"]], dtype=torch.float64, device=dev)
@@ -253,6 +297,13 @@ def run_b200(args):
             td.destroy_process_group()
         return 0
     fp32_peak = nat.fp32_peak_tflops()
+    traffic = None          # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_knn_traffic.json")))
+        if args.workload == "C4" and world == 1:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -261,7 +312,6 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     flops = pairs * 3.0 * d                      # this rank's launch
     achieved = flops / (stage["knn"] * 1e-3) / 1e12
-    K, L = c.k_den, c.k_link
     E = n * (L - 1)
     esz = 4
     hbm = {   # algorithmic bytes per launch (DESIGN.md "Kernels")
@@ -281,18 +331,20 @@ def run_b200(args):
         "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k_den": K, "k_link": L,
                    "parallelism": f"query-sharded x{world}, aggregation on rank 0" if world > 1 else "single GPU",
                    "l2": "working set (P 240 MB, kNN 1.6 GB, 60M edges) >> 126 MB L2; no flush needed",
-                   "groups": int(c.groups.shape[0]), "clusters": int(c.clusters.shape[0])},
+                   "groups": n_groups, "clusters": n_clusters},
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "ms_each_step": steps_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(round(launches)),
         "clocks": clocks,
-        "roofline": {"kernel": "knn_kernel<float,6,20>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+        "roofline": {"kernel": f"knn_kernel<float,{d}>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                      "pairs_evaluated": pairs, "flop_per_pair": 3 * d, "kernel_ms": stage["knn"],
                      "brute_force_equiv_tflops": (float(n) * n * 3 * d) / (knn_ms * 1e-3) / 1e12 / world,
                      "peak_source": "FP32 FMA issue rate measured in this run (al_fp32_peak_tflops); MEASURED_PEAKS.json has no FP32 figure",
-                     "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak"},
+                     "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak; the kernel is instruction-issue bound "
+                                     "(68% issue-slot utilisation in profiles/r01_knn_c4_ncu_summary.txt): tree pruning and per-query "
+                                     "selection, not distance arithmetic, dominate its instruction stream"},
         "stage_ms": stages_out,
-        "host_timers_ms": {k: round(1e3 * getattr(c, k), 2) for k in ("_transformTime", "_logRhoTime", "_aggregateTime", "_regrTime", "_rejTime", "_totalTime")},
+        "host_timers_ms": host_timers,
         "hbm_passes": others,
     }
     if world == 1 and not args.no_cpu_baseline:
