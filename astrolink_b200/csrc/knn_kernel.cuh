@@ -139,6 +139,9 @@ template <> __device__ __forceinline__ float fma_t<float>(float a, float b, floa
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 template <typename T> __device__ __forceinline__ T inf_t() { return (T)INFINITY; }
+// per-axis gap between an interval [lo, hi] and a point/interval: max(lo - x_hi, x_lo - hi, 0)
+__device__ __forceinline__ float gap_t(float a, float b) { return fmaxf(fmaxf(a, b), 0.f); }
+__device__ __forceinline__ double gap_t(double a, double b) { return fmax(fmax(a, b), 0.0); }
 
 template <typename T> __device__ __forceinline__ T warp_max_t(T v);
 template <> __device__ __forceinline__ float warp_max_t<float>(float v) {
@@ -434,8 +437,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             blo[j] = ok ? lo[(i64)j * cnt + c] : (T)0;
             bhi[j] = ok ? hi_[(i64)j * cnt + c] : (T)0;
             T a = blo[j] - qhi[j], b = qlo[j] - bhi[j];
-            T g = a > b ? a : b;
-            g = g > (T)0 ? g : (T)0;
+            const T g = gap_t(a, b);
             acc = fma_t<T>(g, g, acc);
         }
         const bool pass = ok && acc <= s.bound;
@@ -452,8 +454,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
 #pragma unroll
                 for (int j = 0; j < D; j++) {
                     T a = blo[j] - row[j], b = row[j] - bhi[j];
-                    T g = a > b ? a : b;
-                    g = g > (T)0 ? g : (T)0;
+                    const T g = gap_t(a, b);
                     pd = fma_t<T>(g, g, pd);
                 }
                 if (pass && pd <= row[D]) mask |= 1u << q;
@@ -579,8 +580,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
 #pragma unroll
                 for (int j = 0; j < D; j++) {
                     T a = hdr[j] - s.q[j], b = s.q[j] - hdr[D + j];
-                    T g = a > b ? a : b;
-                    g = g > (T)0 ? g : (T)0;
+                    const T g = gap_t(a, b);
                     acc = fma_t<T>(g, g, acc);
                 }
                 need = __ballot_sync(FULL, acc <= s.worst) & pending_need;

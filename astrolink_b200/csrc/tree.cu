@@ -66,23 +66,72 @@ template <typename T>
 __global__ void __launch_bounds__(256) tree_node_bounds_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
                                                                const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
                                                                u32* bbox_lo, u32* bbox_hi, i64 n, i64 n_leaves, int d) {
-    int lane = threadIdx.x & 31;
-    i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    i64 leaf0 = warp * BOUNDS_CHUNK;
-    if (leaf0 >= n_leaves) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const i64 block_leaf0 = (i64)blockIdx.x * (256 / 32) * BOUNDS_CHUNK;
+    if (block_leaf0 >= n_leaves) return;
+    const i64 block_leaf1 = min(block_leaf0 + (256 / 32) * BOUNDS_CHUNK, n_leaves) - 1;
+    // early rounds: the whole block lies inside one (large) node -> reduce in the block, one atomic set per block
+    const u32 a0 = nodeA[block_leaf0];
+    const bool uniform = a0 == nodeA[block_leaf1];
+    const i64 leaf0 = block_leaf0 + (i64)wib * BOUNDS_CHUNK;
     float mn[MAXD], mx[MAXD];
+#pragma unroll
+    for (int j = 0; j < MAXD; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    auto accumulate = [&](i64 leaf) {
+        const i64 p = leaf * LEAF + lane;
+        if (p < n) {
+            const T* row = P + (i64)perm[p] * d;
+#pragma unroll
+            for (int j = 0; j < MAXD; j++)
+                if (j < d) {
+                    const float v = (float)row[j];
+                    mn[j] = fminf(mn[j], v);
+                    mx[j] = fmaxf(mx[j], v);
+                }
+        }
+    };
+    auto warp_reduce = [&](int j, float& a, float& b) {
+        a = mn[j];
+        b = mx[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+            b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+    };
+    if (uniform) {
+        if (nodeB[block_leaf0] - a0 <= 1) return;      // a finished node: nothing to do
+        __shared__ float smn[256 / 32][MAXD], smx[256 / 32][MAXD];
+        for (int c = 0; c < BOUNDS_CHUNK; c++) {
+            const i64 leaf = leaf0 + c;
+            if (leaf < n_leaves) accumulate(leaf);
+        }
+#pragma unroll
+        for (int j = 0; j < MAXD; j++)
+            if (j < d) {
+                float a, b;
+                warp_reduce(j, a, b);
+                if (lane == 0) { smn[wib][j] = a; smx[wib][j] = b; }
+            }
+        __syncthreads();
+        if (threadIdx.x < d) {
+            float a = smn[0][threadIdx.x], b = smx[0][threadIdx.x];
+            for (int w = 1; w < 256 / 32; w++) { a = fminf(a, smn[w][threadIdx.x]); b = fmaxf(b, smx[w][threadIdx.x]); }
+            atomicMin(&bbox_lo[(i64)a0 * d + threadIdx.x], f32_to_ordered(a));
+            atomicMax(&bbox_hi[(i64)a0 * d + threadIdx.x], f32_to_ordered(b));
+        }
+        return;
+    }
+    // general case: every warp flushes per run of leaves of the same node
+    if (leaf0 >= n_leaves) return;
     i64 cur = -1;
     auto flush = [&]() {
         if (cur < 0) return;
 #pragma unroll
         for (int j = 0; j < MAXD; j++) {
             if (j < d) {
-                float a = mn[j], b = mx[j];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-                }
+                float a, b;
+                warp_reduce(j, a, b);
                 if (lane == 0) {
                     atomicMin(&bbox_lo[cur * d + j], f32_to_ordered(a));
                     atomicMax(&bbox_hi[cur * d + j], f32_to_ordered(b));
@@ -91,9 +140,9 @@ __global__ void __launch_bounds__(256) tree_node_bounds_kernel(const T* __restri
         }
     };
     for (int c = 0; c < BOUNDS_CHUNK; c++) {
-        i64 leaf = leaf0 + c;
+        const i64 leaf = leaf0 + c;
         if (leaf >= n_leaves) break;
-        u32 a = nodeA[leaf];
+        const u32 a = nodeA[leaf];
         if (nodeB[leaf] - a <= 1) continue;
         if ((i64)a != cur) {
             flush();
@@ -101,46 +150,50 @@ __global__ void __launch_bounds__(256) tree_node_bounds_kernel(const T* __restri
 #pragma unroll
             for (int j = 0; j < MAXD; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
         }
-        i64 p = leaf * LEAF + lane;
-        if (p < n) {
-            const T* row = P + (i64)perm[p] * d;
-#pragma unroll
-            for (int j = 0; j < MAXD; j++)
-                if (j < d) {
-                    float v = (float)row[j];
-                    mn[j] = fminf(mn[j], v);
-                    mx[j] = fmaxf(mx[j], v);
-                }
-        }
+        accumulate(leaf);
     }
     flush();
+}
+
+// per node being split: widest axis, its lower bound and the quantisation scale of the sort key
+__global__ void __launch_bounds__(256) tree_node_split_info_kernel(const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
+                                                                   const u32* __restrict__ bbox_lo, const u32* __restrict__ bbox_hi,
+                                                                   int* __restrict__ sdim, float* __restrict__ slo,
+                                                                   float* __restrict__ sscale, i64 n_leaves, int d, int cbits) {
+    i64 leaf = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    const u32 a = nodeA[leaf];
+    if (a != (u32)leaf || nodeB[leaf] - a <= 1) return;
+    auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
+    int dim = 0;
+    float best = -1.f, blo = 0.f, bext = 0.f;
+    for (int j = 0; j < d; j++) {
+        const float lo = dec(bbox_lo[(i64)a * d + j]), hi = dec(bbox_hi[(i64)a * d + j]);
+        float ext = hi - lo;
+        ext = ext > 0.f ? ext : 0.f;
+        if (ext > best) { best = ext; dim = j; blo = lo; bext = ext; }
+    }
+    sdim[leaf] = dim;
+    slo[leaf] = blo;
+    sscale[leaf] = bext > 0.f ? (float)((1u << cbits) - 1u) / bext : 0.f;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
                                                              const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
-                                                             const u32* __restrict__ bbox_lo, const u32* __restrict__ bbox_hi,
-                                                             u32* keys, i64 n, int d, int cbits) {
+                                                             const int* __restrict__ sdim, const float* __restrict__ slo,
+                                                             const float* __restrict__ sscale, u32* keys, i64 n, int d, int cbits) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    i64 leaf = p / LEAF;
-    u32 a = nodeA[leaf];
+    const i64 leaf = p / LEAF;
+    const u32 a = nodeA[leaf];
     u32 low;
     if (nodeB[leaf] - a > 1) {
-        int dim = 0;
-        float best = -1.f, blo = 0.f, bext = 0.f;
-        auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
-        for (int j = 0; j < d; j++) {
-            const float lo = dec(bbox_lo[(i64)a * d + j]), hi = dec(bbox_hi[(i64)a * d + j]);
-            float ext = hi - lo;
-            ext = ext > 0.f ? ext : 0.f;
-            if (ext > best) { best = ext; dim = j; blo = lo; bext = ext; }
-        }
-        // the coordinate along the widest axis, quantised to cbits within the node's box: the tree only
+        // the coordinate along the node's widest axis, quantised to cbits within the node's box: the tree only
         // needs a balanced partition of reasonable quality, so ties inside one quantum may fall either side
-        const float x = (float)P[(i64)perm[p] * d + dim];
+        const float x = (float)P[(i64)perm[p] * d + sdim[a]];
         const float top = (float)((1u << cbits) - 1u);
-        float qf = bext > 0.f ? (x - blo) / bext * top : 0.f;
+        float qf = (x - slo[a]) * sscale[a];
         qf = qf < 0.f ? 0.f : (qf > top ? top : qf);
         low = (u32)qf;
     } else {
@@ -223,6 +276,8 @@ struct BuildWs {
     u32 *vals1;
     u32 *nodeA, *nodeB;
     u32 *bbox_lo, *bbox_hi;
+    int* sdim;
+    float *slo, *sscale;
     void* cub_tmp;
     size_t cub_bytes;
 };
@@ -255,6 +310,9 @@ extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
     s.add<u32>(n_leaves);
     s.add<u32>(n_leaves * d);
     s.add<u32>(n_leaves * d);
+    s.add<int>(n_leaves);
+    s.add<float>(n_leaves);
+    s.add<float>(n_leaves);
     s.add<char>(sort_temp_bytes(n));
     return s.off + 256;
 }
@@ -272,6 +330,9 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     w.nodeB = ar.get<u32>(n_leaves);
     w.bbox_lo = ar.get<u32>(n_leaves * d);
     w.bbox_hi = ar.get<u32>(n_leaves * d);
+    w.sdim = ar.get<int>(n_leaves);
+    w.slo = ar.get<float>(n_leaves);
+    w.sscale = ar.get<float>(n_leaves);
     w.cub_bytes = sort_temp_bytes(n);
     w.cub_tmp = ar.get<char>(w.cub_bytes);
     AL_REQUIRE(ar.ok, AL_ENOMEM, "al_index_build: workspace too small (%zu bytes given)", ws_bytes);
@@ -294,12 +355,15 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     for (int r = 0; r < rounds; r++) {
         AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
         AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
-        i64 n_warps = (n_leaves + BOUNDS_CHUNK - 1) / BOUNDS_CHUNK;
-        tree_node_bounds_kernel<T><<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, st>>>(
+        const i64 leaves_per_block = (256 / 32) * BOUNDS_CHUNK;
+        tree_node_bounds_kernel<T><<<(unsigned)((n_leaves + leaves_per_block - 1) / leaves_per_block), 256, 0, st>>>(
             P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, n, n_leaves, d);
         AL_CHECK_LAUNCH();
+        tree_node_split_info_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, w.sdim,
+                                                                                       w.slo, w.sscale, n_leaves, d, cbits);
+        AL_CHECK_LAUNCH();
         tree_make_keys_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, keys[cur], n, d, cbits);
+            P, vals[cur], w.nodeA, w.nodeB, w.sdim, w.slo, w.sscale, keys[cur], n, d, cbits);
         AL_CHECK_LAUNCH();
         size_t tb = w.cub_bytes;
         AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
