@@ -172,3 +172,20 @@ def test_properties_at_one_million_points():
     from oracle import oracle
     od2, oidx = oracle.knn(P, 20, q_begin=0, q_end=300, brute=True)
     assert (idx[:300] == oidx).all() and (d2[:300] == od2).all()
+
+
+def test_object_pickles_like_the_reference(tmp_path):
+    """The reference's io.saveAstroLinkObject pickles the whole object (io.py:25): no live
+    CUDA handles may be left in its state."""
+    import pickle
+    from astrolink_b200 import AstroLink, synth
+    P = synth.two_gaussians(3000, 2, 5, np.float64)
+    c = AstroLink(P)
+    c.run()
+    c2 = pickle.loads(pickle.dumps(c))
+    for name in ("logRho", "ordering", "groups", "prominences", "groups_sigs", "clusters", "significances"):
+        assert np.array_equal(getattr(c2, name), getattr(c, name)), name
+    assert list(c2.ids) == list(c.ids) and c2.S == c.S and c2.k_link == c.k_link
+    np.savez(tmp_path / "obj.npz", clusterer=c)
+    c3 = np.load(tmp_path / "obj.npz", allow_pickle=True)["clusterer"].item()
+    assert np.array_equal(c3.ordering, c.ordering)
