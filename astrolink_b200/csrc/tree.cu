@@ -14,6 +14,7 @@
 #include <unordered_map>
 
 #include "index.cuh"
+#include <stdlib.h>
 
 constexpr int MAXD = 16;
 
@@ -202,14 +203,18 @@ __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict
     keys[p] = (a << cbits) | low;
 }
 
-__global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves) {
+// After a round's sort every node is ordered along its widest axis, so the same order serves `levels`
+// successive cuts: the node is divided into up to 2^levels quantile slabs at the aligned split positions.
+__global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves, int levels) {
     i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_leaves) return;
     u32 a = nodeA[l], b = nodeB[l];
-    if (b - a > 1) {
+    for (int s = 0; s < levels && b - a > 1; s++) {
         u32 mid = split_mid(a, b);
-        if ((u32)l < mid) nodeB[l] = mid; else nodeA[l] = mid;
+        if ((u32)l < mid) b = mid; else a = mid;
     }
+    nodeA[l] = a;
+    nodeB[l] = b;
 }
 
 // one warp per leaf: gather the leaf's points into its tile
@@ -346,7 +351,21 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     tree_init_kernel<<<al_grid(n, 256), 256, 0, st>>>(perm, w.nodeA, w.nodeB, n, n_leaves);
     AL_CHECK_LAUNCH();
 
-    int rounds = tree_depth(n_leaves);
+    const int depth = tree_depth(n_leaves);
+    // Split levels served by one sort.  After a sort a node is ordered along its widest axis, so the same
+    // order can serve several cuts (quantile slabs).  Measured on B200: in <= 3-D three levels per sort are
+    // best throughout; in higher dimensions slabs cost search time near the leaves, so the upper levels take
+    // two per sort and the last 7 levels (128-leaf subtrees) one each.  AL_TREE_LEVELS / AL_TREE_TOP override.
+    int top_levels = d <= 3 ? 3 : 2;
+    int top_rounds = d <= 3 ? 64 : (depth > 7 ? (depth - 7) / 2 : 0);
+    if (const char* e = getenv("AL_TREE_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 8) top_levels = v; }
+    if (const char* e = getenv("AL_TREE_TOP")) { int v = atoi(e); if (v >= 0 && v <= 64) top_rounds = v; }
+    int sched[64];
+    int rounds = 0;
+    for (int done = 0; done < depth && rounds < 64; rounds++) {
+        sched[rounds] = rounds < top_rounds ? top_levels : 1;
+        done += sched[rounds];
+    }
     int node_bits = 1;
     while (((i64)1 << node_bits) < n_leaves) node_bits++;
     int cbits = 32 - node_bits;          // quantised-coordinate bits of the 32-bit sort key
@@ -369,7 +388,7 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
         AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
                                                 cbits + node_bits, st));
         cur ^= 1;
-        tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves);
+        tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves, sched[r]);
         AL_CHECK_LAUNCH();
     }
     if (vals[cur] != perm) AL_CUDA(cudaMemcpyAsync(perm, vals[cur], sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
