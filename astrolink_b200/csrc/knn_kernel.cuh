@@ -33,6 +33,9 @@
 #ifndef KNN_ORDER
 #define KNN_ORDER 1            // 1: visit the leaves of a wide node nearest box first
 #endif
+#ifndef KNN_BRUTE
+#define KNN_BRUTE 0            // 1 (microbenchmark only): no pruning, every tile evaluated densely by every warp
+#endif
 #ifndef KNN_STATS
 #define KNN_STATS 0            // 1: maintain the diagnostic counters [3..7] of the stats array
 #endif
@@ -440,9 +443,11 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             const T g = gap_t(a, b);
             acc = fma_t<T>(g, g, acc);
         }
-        const bool pass = ok && acc <= s.bound;
+        const bool pass = ok && (KNN_BRUTE || acc <= s.bound);
         u32 mask = 0;
-        if (__any_sync(FULL, pass)) {
+        if (KNN_BRUTE) {
+            mask = pass ? qmask : 0u;
+        } else if (__any_sync(FULL, pass)) {
             u32 m = qmask;
 #pragma unroll 1
             while (m) {
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 if (KNN_STATS) { n_needy += __popc(need); n_slow += __popc(need); }
             }
             const int n_need = __popc(need);
-            if (n_need > SPARSE_MAX) {
+            if (KNN_BRUTE || n_need > SPARSE_MAX) {
                 // ---- dense: every lane evaluates all 32 candidates (packed f32x2)
                 n_eval++;
                 n_pairs += (unsigned long long)LEAF * 32;
