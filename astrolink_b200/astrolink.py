@@ -120,7 +120,7 @@ class AstroLink:
         nat.lib()
         assert self.n_samples < 2 ** 31 - 1, "astrolink_b200 supports up to 2**31 - 2 points (uint32 indices)"
         assert self.P.dtype in (np.float32, np.float64), "astrolink_b200 supports float32 / float64 input"
-        assert self.d_features <= 8, "astrolink_b200 supports up to 8 features in this release"
+        assert self.d_features <= 16, "astrolink_b200 supports up to 16 features in this release"
         assert self.k_den <= 128, "astrolink_b200 supports k_den <= 128 in this release"
         self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._dist = dist

@@ -37,7 +37,7 @@ def _units():
         if os.path.exists(os.path.join(CSRC, f)):
             units.append((f, [], f[:-3] + ".o"))
     for tname, t in (("f32", "float"), ("f64", "double")):
-        for d in range(1, 9):
+        for d in range(1, 17):
             units.append(("knn_inst.cu", [f"-DKNN_T={t}", f"-DKNN_TNAME={tname}", f"-DKNN_D={d}"], f"knn_{tname}_d{d}.o"))
     return units
 

@@ -2,15 +2,19 @@
 #include "knn_kernel.cuh"
 
 #define DECL(T, D) int knn_launch_##T##_d##D(const KnnParams& p, cudaStream_t st);
-#define DECL_ALL(T) DECL(T, 1) DECL(T, 2) DECL(T, 3) DECL(T, 4) DECL(T, 5) DECL(T, 6) DECL(T, 7) DECL(T, 8)
+#define DECL_ALL(T) DECL(T, 1) DECL(T, 2) DECL(T, 3) DECL(T, 4) DECL(T, 5) DECL(T, 6) DECL(T, 7) DECL(T, 8) \
+    DECL(T, 9) DECL(T, 10) DECL(T, 11) DECL(T, 12) DECL(T, 13) DECL(T, 14) DECL(T, 15) DECL(T, 16)
 DECL_ALL(f32)
 DECL_ALL(f64)
 
+constexpr int KNN_MAX_D = 16;
 typedef int (*knn_fn)(const KnnParams&, cudaStream_t);
-static const knn_fn g_knn_f32[8] = {knn_launch_f32_d1, knn_launch_f32_d2, knn_launch_f32_d3, knn_launch_f32_d4,
-                                    knn_launch_f32_d5, knn_launch_f32_d6, knn_launch_f32_d7, knn_launch_f32_d8};
-static const knn_fn g_knn_f64[8] = {knn_launch_f64_d1, knn_launch_f64_d2, knn_launch_f64_d3, knn_launch_f64_d4,
-                                    knn_launch_f64_d5, knn_launch_f64_d6, knn_launch_f64_d7, knn_launch_f64_d8};
+#define TAB(T) {knn_launch_##T##_d1, knn_launch_##T##_d2, knn_launch_##T##_d3, knn_launch_##T##_d4, knn_launch_##T##_d5, \
+                knn_launch_##T##_d6, knn_launch_##T##_d7, knn_launch_##T##_d8, knn_launch_##T##_d9, knn_launch_##T##_d10, \
+                knn_launch_##T##_d11, knn_launch_##T##_d12, knn_launch_##T##_d13, knn_launch_##T##_d14, knn_launch_##T##_d15, \
+                knn_launch_##T##_d16}
+static const knn_fn g_knn_f32[KNN_MAX_D] = TAB(f32);
+static const knn_fn g_knn_f64[KNN_MAX_D] = TAB(f64);
 
 extern "C" size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k) {
     (void)dtype; (void)n; (void)d; (void)k;
@@ -28,7 +32,7 @@ extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int
     }
     AL_REQUIRE(k >= 1 && k <= h.n, AL_EINVAL, "al_knn: k must be in [1, n]");
     AL_REQUIRE(k <= 128, AL_EINVAL, "al_knn: k > 128 is not supported");
-    AL_REQUIRE(h.d >= 1 && h.d <= 8, AL_EINVAL, "al_knn: d=%d not supported (1..8)", h.d);
+    AL_REQUIRE(h.d >= 1 && h.d <= KNN_MAX_D, AL_EINVAL, "al_knn: d=%d not supported (1..%d)", h.d, KNN_MAX_D);
     i64 np = h.n_leaves * LEAF;
     AL_REQUIRE(pos_begin >= 0 && pos_begin <= pos_end && pos_end <= np, AL_EINVAL, "al_knn: bad position range");
     AL_REQUIRE(pos_begin % LEAF == 0 && pos_end % LEAF == 0, AL_EINVAL, "al_knn: positions must be multiples of %d", LEAF);

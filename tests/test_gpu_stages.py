@@ -98,7 +98,8 @@ def test_rescale_vs_golden(name, golden):
 
 @pytest.mark.parametrize("n,d,dtype,k", [(20000, 3, np.float32, 20), (30011, 6, np.float32, 20), (5000, 2, np.float64, 9),
                                          (12345, 6, np.float64, 20), (40000, 1, np.float32, 18), (9000, 8, np.float32, 33),
-                                         (3000, 4, np.float32, 100), (33, 3, np.float32, 5), (31, 2, np.float32, 31),
+                                         (3000, 4, np.float32, 100), (33, 3, np.float32, 5), (31, 2, np.float32, 31), (6000, 11, np.float32, 20), (4000, 16, np.float64, 12),
+                                         (5000, 9, np.float64, 20), (7000, 16, np.float32, 25),
                                          (100000, 6, np.float32, 20)])
 def test_knn_vs_oracle_random(n, d, dtype, k):
     from oracle import oracle
