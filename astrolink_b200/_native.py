@@ -44,6 +44,9 @@ _SIGS = {
     "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
     "al_fp32_peak_tflops": (_int, [_vp, _vp]),
     "al_launch_count": (_i64, []),
+    "al_w1_workspace_bytes": (_sz, [_i64]),
+    "al_w1_prepare": (_int, [_vp, _int, _i64, _int, _int, _vp, _sz, _vp, _vp]),
+    "al_w1_eval": (_int, [_vp, _sz, _i64, _c.c_double, _c.c_double, _vp, _vp]),
     "al_significance": (_int, [_vp, _int, _i64, _c.c_double, _c.c_double, _vp, _vp]),
 }
 
@@ -251,6 +254,25 @@ def significance(prom, a, b):
     out = torch.empty(prom.shape, dtype=torch.float64, device=prom.device)
     _check(L.al_significance(_ptr(prom), _dt(prom), prom.numel(), float(a), float(b), _ptr(out), _stream()), "al_significance")
     return out
+
+
+class W1Objective:
+    """f1: GPU evaluation of the fit objective; `sorted` holds the sorted prominences (host, float64)."""
+
+    def __init__(self, prom, col=1):
+        L = lib()
+        assert prom.dim() == 2 and prom.is_contiguous()
+        self.G = prom.shape[0]
+        self.ws = _ws(L.al_w1_workspace_bytes(self.G), prom.device)
+        self.sorted = np.empty(self.G, dtype=np.float64)
+        _check(L.al_w1_prepare(_ptr(prom), _dt(prom), self.G, prom.shape[1], col, _ptr(self.ws), self.ws.numel(),
+                               self.sorted.ctypes.data_as(ctypes.c_void_p), _stream()), "al_w1_prepare")
+        self._val = ctypes.c_double(0.0)
+
+    def __call__(self, p):
+        _check(lib().al_w1_eval(_ptr(self.ws), self.ws.numel(), self.G, float(p[0]), float(p[1]), ctypes.byref(self._val), _stream()),
+               "al_w1_eval")
+        return float(self._val.value)
 
 
 def launch_count():

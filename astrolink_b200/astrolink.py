@@ -394,7 +394,13 @@ class AstroLink:
         start = time.perf_counter()
         self._finish_fetch(("groups", "prominences"))
         prom = self.prominences
-        self.pFit, ok = stats.fit_prominence_model(prom[:, 1])
+        if prom.shape[0] >= 16384:
+            # large group counts: the O(G) objective is evaluated on the GPU, SciPy still drives the fit
+            with torch.cuda.device(self._device):
+                obj = nat.W1Objective(self._dev("prominences"))
+                self.pFit, ok = stats.fit_prominence_model(None, objective=obj, p_sorted=obj.sorted)
+        else:
+            self.pFit, ok = stats.fit_prominence_model(prom[:, 1])
         if not ok:
             self._printFunction('[Warning] Prominence model fitting failed to converge!', returnLine=False, urgent=True)
         with torch.cuda.device(self._device):

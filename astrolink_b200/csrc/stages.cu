@@ -516,3 +516,129 @@ extern "C" int al_significance(const void* prominences, int dtype, int64_t count
     AL_CHECK_LAUNCH();
     return AL_OK;
 }
+
+// ---------------------------------------------------------------------------
+// f1: objective of the prominence-model fit (astrolink.py:880-885, 896-907).
+// The optimiser (SciPy L-BFGS-B, jac='3-point') stays on the host; only the O(G)
+// evaluation of the Wasserstein-1 distance between the numerical cdf of Beta(a, b)
+// and the empirical cdf runs here.  al_w1_prepare sorts the prominences and builds
+// the per-gap tables once; al_w1_eval is called once per objective evaluation.
+// ---------------------------------------------------------------------------
+struct W1Ws {
+    double *p_sorted, *log_mid, *log_omm, *widths, *mass, *partial, *keys_in;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+constexpr int W1_BLOCKS = 592;
+
+static size_t w1_cub_bytes(i64 G) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, a, (const double*)nullptr, (double*)nullptr, G, 0, 64, (cudaStream_t)0);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const double*)nullptr, (double*)nullptr, G, (cudaStream_t)0);
+    return a > b ? a : b;
+}
+static bool w1_layout(void* ws, size_t ws_bytes, i64 G, W1Ws* w) {
+    Arena ar(ws, ws_bytes);
+    w->p_sorted = ar.get<double>(G);
+    w->log_mid = ar.get<double>(G);
+    w->log_omm = ar.get<double>(G);
+    w->widths = ar.get<double>(G);
+    w->mass = ar.get<double>(G);
+    w->keys_in = ar.get<double>(G);
+    w->partial = ar.get<double>(W1_BLOCKS);
+    w->cub_bytes = w1_cub_bytes(G);
+    w->cub_tmp = ar.get<char>(w->cub_bytes);
+    return ar.ok;
+}
+extern "C" size_t al_w1_workspace_bytes(int64_t G) {
+    ArenaSizer s;
+    for (int i = 0; i < 6; i++) s.add<double>(G);
+    s.add<double>(W1_BLOCKS);
+    s.add<char>(w1_cub_bytes(G));
+    return s.off + 256;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) w1_column_kernel(const T* __restrict__ prom, i64 G, int stride, int col, double* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (i64)gridDim.x * blockDim.x) out[i] = (double)prom[i * stride + col];
+}
+__global__ void __launch_bounds__(256) w1_tables_kernel(const double* __restrict__ p, i64 G, double* __restrict__ log_mid,
+                                                        double* __restrict__ log_omm, double* __restrict__ widths) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (i64)gridDim.x * blockDim.x) {
+        const double lo = i == 0 ? 0.0 : p[i - 1], hi = p[i];
+        const double w = hi - lo, mid = 0.5 * (hi + lo);
+        widths[i] = w;
+        // a midpoint of exactly 0 (or 1) only occurs in a zero-width gap, whose mass is 0 anyway
+        log_mid[i] = w > 0.0 ? log(mid) : 0.0;
+        log_omm[i] = w > 0.0 ? log1p(-mid) : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) w1_mass_kernel(const double* __restrict__ log_mid, const double* __restrict__ log_omm,
+                                                      const double* __restrict__ widths, i64 G, double am1, double bm1, double lbeta,
+                                                      double* __restrict__ mass) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (i64)gridDim.x * blockDim.x)
+        mass[i] = exp(am1 * log_mid[i] + bm1 * log_omm[i] - lbeta) * widths[i];
+}
+__global__ void __launch_bounds__(256) w1_distance_kernel(const double* __restrict__ cdf, const double* __restrict__ widths, i64 G,
+                                                          double q0, double qstep, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (i64)gridDim.x * blockDim.x)
+        acc += fabs(cdf[i] - (q0 + (double)i * qstep)) * widths[i];
+    __shared__ double sm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += sm[w];
+        partial[blockIdx.x] = v;
+    }
+}
+__global__ void w1_finish_kernel(const double* __restrict__ partial, int blocks, double* out) {
+    double v = 0.0;
+    for (int b = 0; b < blocks; b++) v += partial[b];
+    out[0] = v;
+}
+
+extern "C" int al_w1_prepare(const void* prominences, int dtype, int64_t G, int stride, int col, void* ws, size_t ws_bytes,
+                             double* sorted_host, void* stream) {
+    AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_w1_prepare: bad dtype");
+    AL_REQUIRE(G >= 1 && stride >= 1 && col >= 0 && col < stride, AL_EINVAL, "al_w1_prepare: bad shape");
+    W1Ws w;
+    AL_REQUIRE(w1_layout(ws, ws_bytes, G, &w), AL_ENOMEM, "al_w1_prepare: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = al_grid(G, 256, W1_BLOCKS);
+    if (dtype == AL_F32) w1_column_kernel<float><<<grid, 256, 0, st>>>((const float*)prominences, G, stride, col, w.keys_in);
+    else w1_column_kernel<double><<<grid, 256, 0, st>>>((const double*)prominences, G, stride, col, w.keys_in);
+    AL_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    AL_CUDA(cub::DeviceRadixSort::SortKeys(w.cub_tmp, tb, w.keys_in, w.p_sorted, G, 0, 64, st));
+    w1_tables_kernel<<<grid, 256, 0, st>>>(w.p_sorted, G, w.log_mid, w.log_omm, w.widths);
+    AL_CHECK_LAUNCH();
+    if (sorted_host) AL_CUDA(cudaMemcpyAsync(sorted_host, w.p_sorted, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    return AL_OK;
+}
+
+extern "C" int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double b, double* value_host, void* stream) {
+    AL_REQUIRE(G >= 1 && a > 0.0 && b > 0.0 && value_host != nullptr, AL_EINVAL, "al_w1_eval: bad arguments");
+    W1Ws w;
+    AL_REQUIRE(w1_layout(ws, ws_bytes, G, &w), AL_ENOMEM, "al_w1_eval: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = al_grid(G, 256, W1_BLOCKS);
+    const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+    w1_mass_kernel<<<grid, 256, 0, st>>>(w.log_mid, w.log_omm, w.widths, G, a - 1.0, b - 1.0, lbeta, w.mass);
+    AL_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    AL_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, w.mass, w.mass, G, st));
+    const double half = 1.0 / (2.0 * (double)G);
+    const double qstep = G > 1 ? (1.0 - 2.0 * half) / (double)(G - 1) : 0.0;
+    w1_distance_kernel<<<grid, 256, 0, st>>>(w.mass, w.widths, G, half, qstep, w.partial);
+    AL_CHECK_LAUNCH();
+    w1_finish_kernel<<<1, 1, 0, st>>>(w.partial, grid, w.keys_in);
+    AL_CHECK_LAUNCH();
+    AL_CUDA(cudaMemcpyAsync(value_host, w.keys_in, sizeof(double), cudaMemcpyDeviceToHost, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    return AL_OK;
+}

@@ -60,13 +60,17 @@ class _W1Objective:
         return float(np.sum(np.abs(cdf - self.quantiles) * self.widths))
 
 
-def fit_prominence_model(prom_leq):
-    """Returns (pFit [2], success).  astrolink.py:848-853."""
-    p_sorted = np.sort(np.asarray(prom_leq, dtype=np.float64))
+def fit_prominence_model(prom_leq, objective=None, p_sorted=None):
+    """Returns (pFit [2], success).  astrolink.py:848-853.  `objective` / `p_sorted` let the caller
+    supply an evaluator of the same function (the GPU one of al_w1_eval) and the sorted values."""
+    if p_sorted is None:
+        p_sorted = np.sort(np.asarray(prom_leq, dtype=np.float64))
     N = p_sorted.size
     guess = _initial_beta_guess(p_sorted)
     tol = 10.0 ** (-np.ceil(np.log10(N)) - 3)
-    sol = minimize(_W1Objective(p_sorted), guess, jac="3-point", bounds=((1, np.inf), (1, np.inf)), tol=tol)
+    if objective is None:
+        objective = _W1Objective(p_sorted)
+    sol = minimize(objective, guess, jac="3-point", bounds=((1, np.inf), (1, np.inf)), tol=tol)
     if sol.success:
         return np.asarray(sol.x, dtype=np.float64), True
     return guess, False

@@ -135,6 +135,17 @@ int al_aggregate(const void* logrho, int dtype, const uint32_t* sorted_pairs, in
  * are the Beta parameters fitted on the host; the fit itself stays in Python. */
 int al_significance(const void* prominences, int dtype, int64_t count, double a, double b, double* sig_out, void* stream);
 
+/* ---- f1: objective of the Beta prominence-model fit (astrolink.py:880-885, 896-907) ----
+ * The optimiser stays on the host (SciPy); these evaluate its O(G) objective.
+ * al_w1_prepare: sorts column `col` of the [G][stride] prominence array (`dtype`), builds
+ * the midpoint tables in `ws`, copies the sorted values (float64) to sorted_host (HOST, may
+ * be NULL).  al_w1_eval: the Wasserstein-1 distance between the midpoint-rule cdf of
+ * Beta(a, b) and the empirical cdf, written to *value_host (HOST).  Both synchronous. */
+size_t al_w1_workspace_bytes(int64_t G);
+int al_w1_prepare(const void* prominences, int dtype, int64_t G, int stride, int col, void* ws, size_t ws_bytes,
+                  double* sorted_host, void* stream);
+int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double b, double* value_host, void* stream);
+
 /* ---- helpers ------------------------------------------------------------ */
 /* scatter rows: dst[perm[p]][0..cols) = src[p][0..cols) for p in [0, rows), skipping
  * perm == 0xffffffff; elem_bytes is 4 or 8. */

@@ -133,3 +133,24 @@ def test_significance_kernel_vs_scipy(a, b):
     got32 = nat.significance(_cu(x32), a, b).cpu().numpy()
     fin = np.isfinite(ref32)
     assert np.allclose(got32[fin], ref32[fin], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("G,dtype", [(50000, np.float32), (20001, np.float64), (300000, np.float32)])
+def test_w1_objective_kernel_vs_numpy(G, dtype):
+    """al_w1_prepare / al_w1_eval == the NumPy objective of astrolink_b200.stats (astrolink.py:896-907),
+    and the fit driven by it lands on the same parameters."""
+    from astrolink_b200 import stats
+    nat = _native()
+    rng = np.random.default_rng(G)
+    prom = np.stack([rng.beta(2.0, 9.0, G), rng.beta(1.4, 11.0, G)], axis=1).astype(dtype)
+    prom[:5, 1] = 0.0                      # zero-width gaps
+    obj = nat.W1Objective(_cu(prom))
+    ps = np.sort(prom[:, 1].astype(np.float64))
+    assert np.array_equal(obj.sorted, ps)
+    ref = stats._W1Objective(ps)
+    for p in ([1.4, 11.0], [1.0, 1.0], [2.5, 30.0], [1.05, 4.0]):
+        a, b = ref(np.array(p)), obj(np.array(p))
+        assert abs(a - b) <= 1e-10 * max(1.0, abs(a)), (p, a, b)
+    f_ref, ok1 = stats.fit_prominence_model(prom[:, 1])
+    f_gpu, ok2 = stats.fit_prominence_model(None, objective=obj, p_sorted=obj.sorted)
+    assert ok1 and ok2 and np.allclose(f_ref, f_gpu, rtol=1e-5)
