@@ -374,24 +374,66 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         la[2 * c + 1] = b;
     });
     {
-        const int rounds = agg_log2_ceil((u64)TL) + 1;
-        uint2_agg* src = la;
-        uint2_agg* dst = lb;
-        for (int r = 0; r < rounds; r++) {
-            const uint2_agg* s_ = src;
-            uint2_agg* d_ = dst;
-            x.template launch<TagRank>(TL, AGG_LAMBDA(i64 i) {
-                uint2_agg a = s_[i];
-                if (a.x != NONE) {
-                    uint2_agg b = s_[a.x];
-                    a.y += b.y;
-                    a.x = b.x;
-                }
-                d_[i] = a;
-            });
-            uint2_agg* t = src; src = dst; dst = t;
+        // List ranking (hops to the end of the tour) in O(TL) work: a pseudo-random 1/32 of the elements
+        // (by a hash of the index: exits have odd indices, chains have regular strides, so a plain modulus
+        // would leave long ruler-free runs) and the head are rulers; each ruler walks to the next ruler
+        // labelling the elements it passes (owner, offset); only the short list of rulers is ranked by
+        // pointer jumping; the ranks of all elements follow.
+        u32* headp = ar.get<u32>(1);
+        u32* rflag2 = ar.get<u32>(TL + 1);
+        u32* rid = ar.get<u32>(TL + 1);
+        if (!ar.ok) return -2;
+        x.template launch<TagMisc>(1, AGG_LAMBDA(i64) { headp[0] = 2u * roots[0]; });
+        x.template launch<TagRank>(TL, AGG_LAMBDA(i64 e) {
+            u32 h = (u32)e * 2654435761u;
+            h ^= h >> 15;
+            rflag2[e] = ((h & 31u) == 0u || (u32)e == headp[0]) ? 1u : 0u;
+        });
+        const i64 nR = x.exclusive_sum_u32(rflag2, rid, TL, ar);
+        u32* relem = ar.get<u32>(nR + 1);
+        uint2_agg* ra = ar.get<uint2_agg>(nR + 1);     // (next ruler id, elements up to the next ruler) ping
+        uint2_agg* rb = ar.get<uint2_agg>(nR + 1);     // pong
+        if (!ar.ok) return -2;
+        x.template launch<TagRank>(TL, AGG_LAMBDA(i64 e) { if (rflag2[e]) relem[rid[e]] = (u32)e; });
+        x.template launch<TagRank>(nR, AGG_LAMBDA(i64 r) {
+            u32 e = relem[r];
+            u32 off = 0;
+            for (;;) {
+                uint2_agg o; o.x = (u32)r; o.y = off;
+                lb[e] = o;
+                const u32 nx = la[e].x;
+                off++;
+                if (nx == NONE) { uint2_agg z; z.x = NONE; z.y = off; ra[r] = z; return; }
+                if (rflag2[nx]) { uint2_agg z; z.x = rid[nx]; z.y = off; ra[r] = z; return; }
+                e = nx;
+            }
+        });
+        // suffix sums of the segment lengths along the ruler list
+        {
+            const int rounds = agg_log2_ceil((u64)nR) + 1;
+            uint2_agg* src = ra;
+            uint2_agg* dst = rb;
+            for (int r = 0; r < rounds; r++) {
+                const uint2_agg* s_ = src;
+                uint2_agg* d_ = dst;
+                x.template launch<TagRank>(nR, AGG_LAMBDA(i64 i) {
+                    uint2_agg a = s_[i];
+                    if (a.x != NONE) {
+                        const uint2_agg b2 = s_[a.x];
+                        a.y += b2.y;
+                        a.x = b2.x;
+                    }
+                    d_[i] = a;
+                });
+                uint2_agg* t = src; src = dst; dst = t;
+            }
+            ra = src;      // ra[rid].y = elements from ruler rid (inclusive) to the end of the tour
         }
-        la = src;   // ranks: hops to the end of the tour
+        const uint2_agg* rs = ra;
+        x.template launch<TagRank>(TL, AGG_LAMBDA(i64 e) {
+            const uint2_agg o = lb[e];
+            la[e].y = rs[o.x].y - 1u - o.y;    // hops from e to the last element
+        });
     }
     x.phase("B-starts");
     // tour position of event e: TL-1 - rank(e); subtree(c) holds (exit-enter+1)/2 internal nodes
