@@ -85,6 +85,19 @@ struct CudaExec {
         note(cudaStreamSynchronize(st));
         ar.reset(mk);
     }
+    void sort_pairs_u32_u32(const u32* k_in, u32* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena& ar) {
+        if (n <= 0) return;
+        if (end_bit < 1) end_bit = 1;
+        if (end_bit > 32) end_bit = 32;
+        const size_t mk = ar.mark();
+        size_t tb = 0;
+        note(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
+        note(cudaStreamSynchronize(st));
+        ar.reset(mk);
+    }
     void sync() { note(cudaStreamSynchronize(st)); }
     void segmented_inclusive_scan(SegItem* items, i64 n, AggArena& ar) {
         if (n <= 0) return;

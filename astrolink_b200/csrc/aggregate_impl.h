@@ -189,25 +189,27 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
             const uint2_agg* e_ = ep;
             const u32* r_ = er;
             const i64 M_ = M;
+            // one pass over the edge list: record the picked edges, and flag the survivors for the next level
+            // (not picked, endpoints in different new components); the keep flag overwrites the pick flag
+            u32* keep = pickflag;
             x.template launch<TagRecord>(m, AGG_LAMBDA(i64 i) {
-                if (!pickflag[i]) return;
-                const i64 c = M_ + pkpos[i];
-                uint2_agg e = e_[i];
-                pk_rank[c] = r_ ? r_[i] : (u32)i;
-                pk_K[c] = label[e.x];
-                pk_p0node[c] = e.x;
-                const bool fx = first[e.x] == (u32)i, fy = first[e.y] == (u32)i;
-                pk_picker[c] = (fx && fy) ? NONE : (fx ? e.x : e.y);
+                const uint2_agg e = e_[i];
+                const u32 lx = label[e.x], ly = label[e.y];
+                if (pickflag[i]) {
+                    const i64 c = M_ + pkpos[i];
+                    pk_rank[c] = r_ ? r_[i] : (u32)i;
+                    pk_K[c] = lx;
+                    pk_p0node[c] = e.x;
+                    const bool fx = first[e.x] == (u32)i, fy = first[e.y] == (u32)i;
+                    pk_picker[c] = (fx && fy) ? NONE : (fx ? e.x : e.y);
+                    keep[i] = 0u;
+                } else {
+                    keep[i] = lx != ly ? 1u : 0u;
+                }
             });
             x.template launch<TagNodeFirst>(N, AGG_LAMBDA(i64 s) {
                 u32 i = first[s];
                 nodefirst[s] = i == NONE ? NONE : (u32)(M_ + pkpos[i]);
-            });
-            // surviving edges: not picked, endpoints in different new components (stable compaction)
-            u32* keep = pickflag;      // reuse: keep flag overwrites pick flag after the records are written
-            x.template launch<TagKeep>(m, AGG_LAMBDA(i64 i) {
-                uint2_agg e = e_[i];
-                keep[i] = (!pickflag[i] && label[e.x] != label[e.y]) ? 1u : 0u;
             });
             const i64 m_next = x.exclusive_sum_u32(keep, pkpos, m, ar);
             uint2_agg* eo = ep_next;
@@ -271,8 +273,10 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 });
             }
         }
-        u64* key_in = ar.get<u64>(cnt);
-        u64* key_out = ar.get<u64>(cnt);
+        // accepted edges of one level are stored in rank order, so a STABLE sort by link alone orders every
+        // chain by rank: 32-bit keys over the bits the link ids need
+        u32* key_in = ar.get<u32>(cnt);
+        u32* key_out = ar.get<u32>(cnt);
         u32* val_in = ar.get<u32>(cnt);
         u32* val_out = ar.get<u32>(cnt);
         if (!ar.ok) return -2;
@@ -291,15 +295,15 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                     link = (u32)(Nup + (cur - hi));
                 }
             }
-            key_in[i] = ((u64)link << 32) | r;
+            key_in[i] = link;
             val_in[i] = (u32)c;
         });
-        x.sort_pairs_u64_u32(key_in, key_out, val_in, val_out, cnt, 64, ar);
+        x.sort_pairs_u32_u32(key_in, key_out, val_in, val_out, cnt, agg_log2_ceil((u64)(Nup + suffix + 1)), ar);
         // pass 1: chain links, and the top of every chain takes over the link's old parent
         x.template launch<TagLink1>(cnt, AGG_LAMBDA(i64 i) {
             const u32 c = val_out[i];
-            const u32 link = (u32)(key_out[i] >> 32);
-            const bool nextsame = (i + 1 < cnt) && (u32)(key_out[i + 1] >> 32) == link;
+            const u32 link = key_out[i];
+            const bool nextsame = (i + 1 < cnt) && key_out[i + 1] == link;
             if (nextsame) {
                 const u32 P = val_out[i + 1];
                 par[c] = P;
@@ -321,9 +325,9 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         });
         // pass 2: the bottom of a chain on an edge link adopts that edge
         x.template launch<TagLink2>(cnt, AGG_LAMBDA(i64 i) {
-            const u32 link = (u32)(key_out[i] >> 32);
+            const u32 link = key_out[i];
             if ((i64)link < Nup) return;
-            if (i > 0 && (u32)(key_out[i - 1] >> 32) == link) return;
+            if (i > 0 && key_out[i - 1] == link) return;
             const u32 c = val_out[i];
             const u32 f = (u32)(hi + ((i64)link - Nup));
             par[f] = c;

@@ -38,6 +38,13 @@ struct HostExec {
         std::stable_sort(idx.begin(), idx.end(), [&](i64 a, i64 b) { return (k_in[a] & mask) < (k_in[b] & mask); });
         for (i64 i = 0; i < n; i++) { k_out[i] = k_in[idx[i]]; v_out[i] = v_in[idx[i]]; }
     }
+    void sort_pairs_u32_u32(const u32* k_in, u32* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena&) {
+        std::vector<i64> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        const u32 mask = end_bit >= 32 ? ~0u : ((1u << end_bit) - 1);
+        std::stable_sort(idx.begin(), idx.end(), [&](i64 a, i64 b) { return (k_in[a] & mask) < (k_in[b] & mask); });
+        for (i64 i = 0; i < n; i++) { k_out[i] = k_in[idx[i]]; v_out[i] = v_in[idx[i]]; }
+    }
     void sync() {}
     void phase(const char*) {}
     void phase_level(const char*, int, i64, i64) {}
