@@ -370,6 +370,7 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     while (((i64)1 << node_bits) < n_leaves) node_bits++;
     int cbits = 32 - node_bits;          // quantised-coordinate bits of the 32-bit sort key
     if (cbits > 16) cbits = 16;
+    if (const char* e = getenv("AL_TREE_CBITS")) { int v = atoi(e); if (v >= 3 && v <= cbits) cbits = v; }   // development knob
     AL_REQUIRE(cbits >= 5, AL_EINVAL, "al_index_build: too many leaves for 32-bit sort keys");
     for (int r = 0; r < rounds; r++) {
         AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
