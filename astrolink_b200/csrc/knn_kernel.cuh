@@ -24,12 +24,6 @@
 #ifndef KNN_SPARSE_MAX
 #define KNN_SPARSE_MAX 12
 #endif
-#ifndef KNN_SPARSE4
-#define KNN_SPARSE4 0          // 1: four needy queries per sparse pass instead of two
-#endif
-#ifndef KNN_REFRESH
-#define KNN_REFRESH 0          // 1: re-test every query against the tile's box with the current k-th distances
-#endif
 #ifndef KNN_ORDER
 #define KNN_ORDER 1            // 1: visit the leaves of a wide node nearest box first
 #endif
@@ -579,18 +573,6 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 qworst[0] = s.worst;
                 __syncwarp();
                 need = FULL;
-            } else if (KNN_REFRESH) {
-                // refresh the need mask with the current k-th distances
-                T acc = (T)0;
-#pragma unroll
-                for (int j = 0; j < D; j++) {
-                    T a = hdr[j] - s.q[j], b = s.q[j] - hdr[D + j];
-                    const T g = gap_t(a, b);
-                    acc = fma_t<T>(g, g, acc);
-                }
-                need = __ballot_sync(FULL, acc <= s.worst) & pending_need;
-                n_needy += __popc(need);
-                n_slow += __popc(pending_need);
             } else {
                 need = pending_need;
                 if (KNN_STATS) { n_needy += __popc(need); n_slow += __popc(need); }
@@ -632,39 +614,9 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 for (int j = 0; j < D; j++) cc[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
                 const u32 cid = ids[lane];
                 u32 m = need;
-#if KNN_SPARSE4
 #pragma unroll 1
                 while (m) {
-                    // up to four needy queries per pass: two packed pairs, independent dependency chains
-                    int qv[4];
-                    bool on[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        on[e] = m != 0;
-                        qv[e] = on[e] ? __ffs(m) - 1 : qv[0];
-                        m &= m - 1;
-                    }
-                    T r0[RS], r1[RS], r2[RS], r3[RS];
-                    load_row<RS>(qtab + qv[0] * RS, r0);
-                    load_row<RS>(qtab + qv[1] * RS, r1);
-                    load_row<RS>(qtab + qv[2] * RS, r2);
-                    load_row<RS>(qtab + qv[3] * RS, r3);
-                    T v0, v1, v2, v3;
-                    pair_dist<D>(r0, r1, cc, v0, v1);
-                    pair_dist<D>(r2, r3, cc, v2, v3);
-                    const u32 h0 = __ballot_sync(FULL, v0 <= r0[D]);
-                    const u32 h1 = on[1] ? __ballot_sync(FULL, v1 <= r1[D]) : 0u;
-                    const u32 h2 = on[2] ? __ballot_sync(FULL, v2 <= r2[D]) : 0u;
-                    const u32 h3 = on[3] ? __ballot_sync(FULL, v3 <= r3[D]) : 0u;
-                    if (h0) emit_hits(h0, v0, cid, qv[0]);
-                    if (h1) emit_hits(h1, v1, cid, qv[1]);
-                    if (h2) emit_hits(h2, v2, cid, qv[2]);
-                    if (h3) emit_hits(h3, v3, cid, qv[3]);
-                }
-#else
-#pragma unroll 1
-                while (m) {
-                    // two needy queries per pass (one packed f32x2 chain)
+                    // two needy queries per pass (two independent scalar chains, see pair_dist)
                     const int qa = __ffs(m) - 1;
                     m &= m - 1;
                     const bool two = m != 0;
@@ -680,7 +632,6 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                     if (ha) emit_hits(ha, va, cid, qa);
                     if (hb) emit_hits(hb, vb, cid, qb);
                 }
-#endif
             }
         }
         if (!lookahead) { pending = -1; continue; }
