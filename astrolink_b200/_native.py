@@ -44,6 +44,12 @@ _SIGS = {
     "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
     "al_fp32_peak_tflops": (_int, [_vp, _vp]),
     "al_launch_count": (_i64, []),
+    "al_peer_alloc": (_int, [_sz, _vp, _vp]),
+    "al_peer_open": (_int, [_vp, _vp]),
+    "al_peer_release": (_int, [_vp, _int]),
+    "al_knn_link": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
+    "al_logrho_rows": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _vp, _vp, _vp]),
+    "al_enable_peer_access": (_int, [_int]),
     "al_w1_workspace_bytes": (_sz, [_i64]),
     "al_w1_prepare": (_int, [_vp, _int, _i64, _int, _int, _vp, _sz, _vp, _vp]),
     "al_w1_eval": (_int, [_vp, _sz, _i64, _c.c_double, _c.c_double, _vp, _vp]),
@@ -144,8 +150,9 @@ class Index:
         """index position -> original point (uint32 viewed as int32 tensor; padding = -1)."""
         return self.buf[256:256 + 4 * self.positions].view(torch.int32)
 
-    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False):
-        """a3: exact kNN of the points at index positions [pos_begin, pos_end)."""
+    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None):
+        """a3: exact kNN of the points at index positions [pos_begin, pos_end).  link_out: optional
+        [n, L] int32 tensor (possibly peer-mapped) that receives the L nearest ids at the original row."""
         L = lib()
         pos_end = self.positions if pos_end is None else pos_end
         rows = self.n if row_order == 0 else pos_end - pos_begin
@@ -153,23 +160,72 @@ class Index:
         d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
         pairs = torch.zeros(8, dtype=torch.int64, device=self.device) if count_pairs else None
         ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)
-        _check(L.al_knn(_ptr(self.buf), pos_begin, pos_end, k, row_order, _ptr(idx), _ptr(d2), _ptr(pairs), _ptr(ws), ws.numel(),
-                        _stream()), "al_knn")
+        link_cols = 0 if link_out is None else int(link_out.shape[1])
+        _check(L.al_knn_link(_ptr(self.buf), pos_begin, pos_end, k, row_order, _ptr(idx), _ptr(d2), _ptr(link_out), link_cols,
+                             _ptr(pairs), _ptr(ws), ws.numel(), _stream()), "al_knn_link")
         if count_pairs:
             return d2, idx, pairs
         return d2, idx
 
 
-def logrho(d2, idx, k_den, d_intrinsic, weights=None):
-    """a4/a5: raw log-density from squared kNN distances."""
+def logrho(d2, idx, k_den, d_intrinsic, weights=None, row_ids=None, out=None):
+    """a4/a5: raw log-density from squared kNN distances.  With row_ids/out, row i goes to out[row_ids[i]]
+    (out may be a peer-mapped tensor)."""
     L = lib()
     nq, k = d2.shape
     assert k == k_den and d2.is_contiguous()
-    out = torch.empty(nq, dtype=d2.dtype, device=d2.device)
+    if out is None:
+        out = torch.empty(nq, dtype=d2.dtype, device=d2.device)
     if weights is not None:
         assert weights.dtype == torch.float64 and idx is not None and idx.is_contiguous()
-    _check(L.al_logrho(_ptr(d2), _ptr(idx), _ptr(weights), _dt(d2), nq, k, int(d_intrinsic), _ptr(out), _stream()), "al_logrho")
+    _check(L.al_logrho_rows(_ptr(d2), _ptr(idx), _ptr(weights), _dt(d2), nq, k, int(d_intrinsic), _ptr(row_ids), _ptr(out), _stream()),
+           "al_logrho_rows")
     return out
+
+
+class PeerArray:
+    """A device array that lives on the owner rank's GPU.  On the owner it also carries `.tensor`, a torch
+    view of the same memory; on the other ranks it is only an address their kernels may store to."""
+
+    _TYPESTR = {torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8"}
+
+    def __init__(self, shape, dtype, handle=None):
+        L = lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        nbytes = int(np.prod(self.shape)) * torch.empty(0, dtype=dtype).element_size()
+        p = ctypes.c_void_p(0)
+        if handle is None:                       # owner: allocate and export
+            buf = (ctypes.c_ubyte * 64)()
+            _check(L.al_peer_alloc(nbytes, ctypes.byref(p), buf), "al_peer_alloc")
+            self.handle = bytes(buf)
+            self.owner = True
+            self.ptr = int(p.value)
+            self.__cuda_array_interface__ = {"shape": self.shape, "typestr": self._TYPESTR[dtype], "data": (self.ptr, False), "version": 2}
+            self.tensor = torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+        else:                                    # peer: map with the current device as the accessing device
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+            _check(L.al_peer_open(buf, ctypes.byref(p)), "al_peer_open")
+            self.handle = handle
+            self.owner = False
+            self.ptr = int(p.value)
+            self.tensor = None
+
+    def data_ptr(self):
+        return self.ptr
+
+    def element_size(self):
+        return torch.empty(0, dtype=self.dtype).element_size()
+
+    def stride(self, i):
+        st = 1
+        for s in self.shape[i + 1:]:
+            st *= s
+        return st
+
+
+def enable_peer_access(peer_device):
+    _check(lib().al_enable_peer_access(int(peer_device)), "al_enable_peer_access")
 
 
 def minmax(x):

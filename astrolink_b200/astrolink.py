@@ -280,7 +280,8 @@ class AstroLink:
                 raw, kNN = self._sharded_knn(index, w, rank, world)
                 a, b = self._stage("density")
                 a.record()
-            lr = nat.normalise_(raw)
+            # with the peer exchange only rank 0 holds the densities (results live on rank 0)
+            lr = nat.normalise_(raw) if (world == 1 or rank == 0 or getattr(self._dist, "peer", None) is None) else raw
             b.record()
             self._set_dev("logRho", lr)
             self._set_dev("kNN", kNN)
@@ -294,6 +295,9 @@ class AstroLink:
         from . import dist as adist
         n, K, L = self.n_samples, self.k_den, self.k_link
         lo, hi, per = adist.shard_positions(index.positions, rank, world, nat.LEAF)
+        peer = getattr(self._dist, "peer", None)
+        if peer is not None:
+            return self._sharded_knn_peer(index, w, rank, lo, hi, peer)
         a, b = self._stage("knn")
         a.record()
         d2, idx, self._knn_pairs = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1, count_pairs=True)
@@ -319,6 +323,29 @@ class AstroLink:
         nat.scatter_rows(knn_all[sel].contiguous(), perm, kNN)
         nat.scatter_rows(raw_all[sel].contiguous().view(-1, 1), perm, raw.view(-1, 1))
         return raw, kNN
+
+    def _sharded_knn_peer(self, index, w, rank, lo, hi, peer):
+        """Exchange fused into the kernels: every rank's kNN epilogue stores the k_link nearest ids, and
+        its density kernel the raw log-density, directly into rank 0's arrays (peer-mapped over NVLink)."""
+        n, K, L = self.n_samples, self.k_den, self.k_link
+        dt = torch.float32 if self.P.dtype == np.float32 else torch.float64
+        knn0 = peer.get("kNN", (n, L), torch.int32, self._device)
+        raw0 = peer.get("logRho_raw", (n,), dt, self._device)
+        a, b = self._stage("knn")
+        a.record()
+        d2, idx, self._knn_pairs = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1, count_pairs=True, link_out=knn0)
+        b.record()
+        row_ids = index.perm()[lo:hi]
+        nat.logrho(d2, idx, K, self.d_intrinsic, weights=w, row_ids=row_ids, out=raw0)
+        del d2, idx
+        a, b = self._stage("all_gather")
+        a.record()
+        torch.cuda.synchronize(self._device)      # this rank's peer stores are complete ...
+        self._dist.barrier()                      # ... and so are everybody else's
+        b.record()
+        if rank != 0:
+            return torch.zeros((n,), dtype=dt, device=self._device), torch.zeros((1, L), dtype=torch.int32, device=self._device)
+        return raw0.tensor.clone(), knn0.tensor.clone()
 
     # ------------------------------------------------------------------ a8-a11
     def aggregate(self):

@@ -23,7 +23,14 @@ extern "C" size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k) {
 
 extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out,
                       void* d2_out, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream) {
+    return al_knn_link(index, pos_begin, pos_end, k, row_order, idx_out, d2_out, nullptr, 0, pairs_evaluated, ws, ws_bytes, stream);
+}
+
+extern "C" int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out,
+                           void* d2_out, uint32_t* link_out, int link_cols, unsigned long long* pairs_evaluated, void* ws,
+                           size_t ws_bytes, void* stream) {
     (void)ws; (void)ws_bytes;
+    AL_REQUIRE(link_out == nullptr || (link_cols >= 1 && link_cols <= k), AL_EINVAL, "al_knn_link: link_cols must be in [1, k]");
     IndexHeader h;
     if (!index_lookup(index, &h)) {
         AL_CUDA(cudaMemcpy(&h, index, sizeof(h), cudaMemcpyDeviceToHost));
@@ -53,6 +60,8 @@ extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int
     p.row_order = row_order;
     p.idx_out = idx_out;
     p.d2_out = d2_out;
+    p.link_out = link_out;
+    p.link_cols = link_cols;
     p.stats = pairs_evaluated;
     cudaStream_t st = (cudaStream_t)stream;
     if (h.dtype == AL_F32) {

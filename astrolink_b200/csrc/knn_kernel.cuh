@@ -62,6 +62,8 @@ struct KnnParams {
     int row_order;
     u32* idx_out;
     void* d2_out;
+    u32* link_out;      // optional [n][link_cols] at the original point index; may live on a peer GPU
+    int link_cols;
     unsigned long long* stats;   // [KNN_NSTATS] or nullptr
     int warp_smem;
 };
@@ -663,6 +665,13 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     } else if (p.row_order == 1) {
 #pragma unroll 1
         for (int m = 0; m < K; m++) { p.idx_out[pos_row * K + m] = 0xffffffffu; ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>(); }
+    }
+    if (p.link_out != nullptr && s.active) {
+        // the exchange step of the multi-GPU path, fused into the epilogue: the k_link nearest ids go
+        // straight to the consumer's buffer (a peer-mapped pointer over NVLink on ranks other than the owner)
+        u32* lo_ = p.link_out + (i64)my_id * p.link_cols;
+#pragma unroll 1
+        for (int m = 0; m < p.link_cols; m++) lo_[m] = KS::id(hk.ld(m * 32 + lane));
     }
     if (p.stats != nullptr) {
         const u32 pushes = __reduce_add_sync(FULL, s.n_push), inserts = __reduce_add_sync(FULL, s.n_insert);

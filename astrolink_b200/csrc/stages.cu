@@ -143,9 +143,15 @@ extern "C" int al_rescale(const void* P, int dtype, int64_t n, int d, int64_t ro
 template <typename T, bool VEC4>
 __global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, const u32* __restrict__ idx,
                                                      const double* __restrict__ weights, i64 nq, int k, double half_d,
-                                                     T* __restrict__ out) {
+                                                     const u32* __restrict__ row_ids, T* __restrict__ out) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
+    i64 orow = i;
+    if (row_ids != nullptr) {
+        const u32 rid = row_ids[i];
+        if (rid == 0xffffffffu) return;      // padding row of the last leaf
+        orow = rid;
+    }
     const T* r = d2 + i * k;
     const T coreT = r[k - 1];
     const double core = (double)coreT;
@@ -172,11 +178,16 @@ __global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, c
         }
         v = (sw - swd / core) / pow(core, half_d);
     }
-    out[i] = (T)log(v);
+    out[orow] = (T)log(v);
 }
 
 extern "C" int al_logrho(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k,
                          int d_intrinsic, void* logrho_out, void* stream) {
+    return al_logrho_rows(d2, idx, weights, dtype, nq, k, d_intrinsic, nullptr, logrho_out, stream);
+}
+
+extern "C" int al_logrho_rows(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k,
+                              int d_intrinsic, const uint32_t* row_ids, void* logrho_out, void* stream) {
     AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_logrho: bad dtype");
     AL_REQUIRE(nq >= 0 && k >= 1 && d_intrinsic >= 1, AL_EINVAL, "al_logrho: bad shape");
     AL_REQUIRE(weights == nullptr || idx != nullptr, AL_EINVAL, "al_logrho: weights need idx");
@@ -185,11 +196,11 @@ extern "C" int al_logrho(const void* d2, const uint32_t* idx, const double* weig
     unsigned grid = (unsigned)((nq + 255) / 256);
     if (dtype == AL_F32) {
         if (k % 4 == 0 && ((uintptr_t)d2 & 15) == 0)
-            logrho_kernel<float, true><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, (float*)logrho_out);
+            logrho_kernel<float, true><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (float*)logrho_out);
         else
-            logrho_kernel<float, false><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, (float*)logrho_out);
+            logrho_kernel<float, false><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (float*)logrho_out);
     } else {
-        logrho_kernel<double, false><<<grid, 256, 0, st>>>((const double*)d2, idx, weights, nq, k, d_intrinsic / 2.0, (double*)logrho_out);
+        logrho_kernel<double, false><<<grid, 256, 0, st>>>((const double*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (double*)logrho_out);
     }
     AL_CHECK_LAUNCH();
     return AL_OK;
@@ -640,5 +651,56 @@ extern "C" int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double
     AL_CHECK_LAUNCH();
     AL_CUDA(cudaMemcpyAsync(value_host, w.keys_in, sizeof(double), cudaMemcpyDeviceToHost, st));
     AL_CUDA(cudaStreamSynchronize(st));
+    return AL_OK;
+}
+
+// peer access from the current device to `peer_device` (multi-GPU path: kernels on rank r store into rank 0's buffers)
+extern "C" int al_enable_peer_access(int peer_device) {
+    int dev = 0;
+    AL_CUDA(cudaGetDevice(&dev));
+    if (dev == peer_device) return AL_OK;
+    int can = 0;
+    AL_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    AL_REQUIRE(can == 1, AL_EINVAL, "al_enable_peer_access: device %d cannot access device %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return AL_OK; }
+    AL_CUDA(e);
+    return AL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Peer buffers of the multi-GPU path: allocated on the consumer GPU (rank 0) and mapped
+// into the other ranks' processes through CUDA IPC, opened with the ACCESSING device
+// current so that its kernels can store into them over NVLink.
+// ---------------------------------------------------------------------------
+extern "C" int al_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle64_host) {
+    AL_REQUIRE(bytes > 0 && ptr_host != nullptr && handle64_host != nullptr, AL_EINVAL, "al_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    AL_CUDA(cudaMalloc(&p, bytes));          // set-up path, not the hot path
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        al_set_error("al_peer_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+        return AL_ECUDA;
+    }
+    memcpy(handle64_host, &h, 64);
+    *ptr_host = p;
+    return AL_OK;
+}
+extern "C" int al_peer_open(const unsigned char* handle64_host, void** ptr_host) {
+    AL_REQUIRE(handle64_host != nullptr && ptr_host != nullptr, AL_EINVAL, "al_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void* p = nullptr;
+    AL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_host = p;
+    return AL_OK;
+}
+extern "C" int al_peer_release(void* ptr, int owner) {
+    if (ptr == nullptr) return AL_OK;
+    if (owner) AL_CUDA(cudaFree(ptr));
+    else AL_CUDA(cudaIpcCloseMemHandle(ptr));
     return AL_OK;
 }

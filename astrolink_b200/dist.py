@@ -28,13 +28,48 @@ def gathered_rows(positions, world, leaf, device):
     return r * per + (pos - r * per)
 
 
-class TorchDist:
-    """Thin adaptor over torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
+class PeerBuffers:
+    """Result buffers that live on rank 0's GPU and are mapped into every other rank's address
+    space through CUDA IPC (torch's shared-storage mechanism).  Kernels on rank r then store their
+    rows straight into rank 0's arrays over NVLink, so the exchange is fused into the compute
+    kernels' epilogues and no collective is needed.  Buffers are cached per (name, shape, dtype)."""
 
-    def __init__(self, group=None):
+    def __init__(self, dist):
+        self.dist = dist
+        self.cache = {}
+
+    def get(self, name, shape, dtype, device):
+        """Collective: every rank calls with identical arguments.  Returns a _native.PeerArray backed by rank 0's
+        memory (on rank 0 its `.tensor` is a torch view of it)."""
+        import torch.distributed as td
+        from . import _native as nat
+        key = (name, tuple(shape), dtype)
+        if key in self.cache:
+            return self.cache[key]
+        rank = self.dist.get_rank()
+        payload = [None]
+        arr = None
+        with torch.cuda.device(device):
+            if rank == 0:
+                arr = nat.PeerArray(shape, dtype)
+                payload = [arr.handle]
+            td.broadcast_object_list(payload, src=0, group=self.dist.group)
+            if rank != 0:
+                arr = nat.PeerArray(shape, dtype, handle=payload[0])
+        self.cache[key] = arr
+        return arr
+
+
+class TorchDist:
+    """Thin adaptor over torch.distributed (NCCL on GPUs, gloo in CPU tests).  peer=True (default):
+    neighbour lists and densities are written by the kernels directly into rank 0's buffers through
+    NVLink peer memory; peer=False: padded shards + NCCL all-gather."""
+
+    def __init__(self, group=None, peer=True):
         import torch.distributed as td
         self.td = td
         self.group = group
+        self.peer = PeerBuffers(self) if peer else None
 
     def get_rank(self):
         return self.td.get_rank(self.group)

@@ -85,6 +85,12 @@ int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row
            uint32_t* idx_out, void* d2_out, unsigned long long* pairs_evaluated,
            void* ws, size_t ws_bytes, void* stream);
 
+/* a3 with the multi-GPU exchange fused in: additionally writes the first `link_cols` neighbour ids of every
+ * query to link_out[original index][link_cols].  link_out may be a peer-mapped pointer into another GPU's
+ * memory (NVLink): the rows then land directly in the consumer's kNN buffer and no all-gather is needed. */
+int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out, void* d2_out,
+                uint32_t* link_out, int link_cols, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- a4/a5: _compute_logRho_njit / _compute_weighted_logRho_njit
  *      (astrolink.py:293-303, gather of weights[indices] at :283) ----------
  * out[i] = log((sum_j w_j - sum_j w_j d2[i][j] / d2[i][k-1]) / d2[i][k-1]^(d_intrinsic/2)),
@@ -92,6 +98,11 @@ int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row
  * float64, stored in `dtype` (as the reference's store at :282). */
 int al_logrho(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq,
               int k, int d_intrinsic, void* logrho_out, void* stream);
+
+/* as al_logrho, but row i is written to logrho_out[row_ids[i]] (row_ids == 0xffffffff: skipped); logrho_out may be
+ * a peer-mapped pointer (multi-GPU: every rank scatters its densities into the consumer's array). */
+int al_logrho_rows(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k, int d_intrinsic,
+                   const uint32_t* row_ids, void* logrho_out, void* stream);
 
 /* ---- a7: _normalise_njit (astrolink.py:305-313) -------------------------
  * x <- (x - min) / (max - min) over all n.  minmax_out (device, 2 values of
@@ -151,6 +162,15 @@ int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double b, double*
  * perm == 0xffffffff; elem_bytes is 4 or 8. */
 int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int cols, int src_stride,
                     int dst_stride, int elem_bytes, void* dst, void* stream);
+/* Peer buffers of the multi-GPU path.  al_peer_alloc: device memory on the current device plus its 64-byte CUDA
+ * IPC handle (both returned through HOST pointers); al_peer_open: maps such a buffer into this process with the
+ * CURRENT device as the accessing device (its kernels may then store into it over NVLink); al_peer_release frees
+ * (owner != 0) or unmaps (owner == 0).  Set-up calls, not on the hot path. */
+int al_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle64_host);
+int al_peer_open(const unsigned char* handle64_host, void** ptr_host);
+int al_peer_release(void* ptr, int owner);
+/* enables peer access from the current device to `peer_device` (idempotent). */
+int al_enable_peer_access(int peer_device);
 /* kernels launched by this library so far in this process (its own kernels; CUB's
  * internal launches are not counted). */
 int64_t al_launch_count(void);

@@ -20,14 +20,20 @@ rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 td.init_process_group("nccl", device_id=torch.device("cuda", local))
 P = synth.halo6d(150001, seed=9, n_sub=32)
-c = AstroLink(P, dist=adist.TorchDist())
-c.run()
+s = None
 if rank == 0:
     s = AstroLink(P)
     s.run()
-    assert (c.logRho == s.logRho).all(), "logRho differs between sharded and single-GPU runs"
-    assert (c.ordering == s.ordering).all() and (c.groups == s.groups).all()
-    assert (c.clusters == s.clusters).all() and list(c.ids) == list(s.ids)
+# peer=True: kernels store into rank 0's buffers over NVLink (run twice: cached mappings); peer=False: NCCL all-gather
+for D in (adist.TorchDist(peer=True), adist.TorchDist(peer=False)):
+    for rep in range(2):
+        c = AstroLink(P, dist=D)
+        c.run()
+        if rank == 0:
+            assert (c.logRho == s.logRho).all(), "logRho differs between sharded and single-GPU runs"
+            assert (c.ordering == s.ordering).all() and (c.groups == s.groups).all()
+            assert (c.clusters == s.clusters).all() and list(c.ids) == list(s.ids)
+if rank == 0:
     print("MULTI_OK", c.clusters.shape[0])
 td.destroy_process_group()
 '''
