@@ -173,6 +173,7 @@ def run_reference(args):
         return 0
     from oracle import oracle
     oracle.build()
+    oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
     P, kwargs, desc = make_workload(args.workload)
     n_s = min(args.cpu_sample, P.shape[0])
     sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
@@ -350,6 +351,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
+    oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
         n_s = min(args.cpu_sample, n)
         sample = np.ascontiguousarray(P[:n_s])
         cpu_hot_path_seconds(sample[:20000], kwargs)

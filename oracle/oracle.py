@@ -58,6 +58,13 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n=None):
+    """Use n host threads (default: all cores) regardless of OMP_NUM_THREADS (torchrun sets it to 1)."""
+    n = (os.cpu_count() or 1) if n is None else int(n)
+    lib().oracle_set_num_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def rescale(P):
     """transform_data / _rescale_njit (astrolink.py:218-243)."""
     P = np.ascontiguousarray(P)
