@@ -217,6 +217,159 @@ __global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves, int leve
     nodeB[l] = b;
 }
 
+
+// ---------------------------------------------------------------------------
+// Bottom of the tree in shared memory: one CTA finishes an aligned block of
+// BOT_LEAVES leaves (a subtree, by the aligned split rule) -- all remaining
+// split levels, one level per pass, tight boxes and widest-axis choice per node
+// exactly as the global rounds do -- without touching global memory in between.
+// Points stay in place in shared memory; only an order array is sorted
+// (cub::BlockRadixSort over (node, quantised coordinate) keys).
+// ---------------------------------------------------------------------------
+constexpr int BOT_LEAVES = 128;
+constexpr int BOT_POINTS = BOT_LEAVES * LEAF;     // 4096
+constexpr int BOT_THREADS = 512;
+constexpr int BOT_ITEMS = BOT_POINTS / BOT_THREADS;
+typedef cub::BlockRadixSort<u32, BOT_THREADS, BOT_ITEMS, u32> BotSort;
+
+static size_t tree_bottom_smem(int d) {
+    return (size_t)BOT_POINTS * d * 4 + (size_t)BOT_POINTS * 4 * 2 + (size_t)BOT_LEAVES * (2 + 2 * d + 4) * 4 + sizeof(BotSort::TempStorage) + 64;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __restrict__ P, u32* perm, i64 n, i64 n_leaves, int d, int cb) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    float* coords = (float*)bsm;                               // [d][BOT_POINTS]
+    u32* ids = (u32*)(coords + (size_t)d * BOT_POINTS);        // [BOT_POINTS] original point ids
+    u32* order = ids + BOT_POINTS;                             // [BOT_POINTS] slot -> local point
+    u32* nA = order + BOT_POINTS;                              // [BOT_LEAVES] node range of every leaf (block-relative)
+    u32* nB = nA + BOT_LEAVES;
+    u32* blo = nB + BOT_LEAVES;                                // [BOT_LEAVES][d] boxes (ordered uints), by node start
+    u32* bhi = blo + BOT_LEAVES * d;
+    int* sdim = (int*)(bhi + BOT_LEAVES * d);                  // [BOT_LEAVES]
+    float* slo = (float*)(sdim + BOT_LEAVES);
+    float* ssc = slo + BOT_LEAVES;
+    u32* nrank = (u32*)(ssc + BOT_LEAVES);                     // [BOT_LEAVES] rank of the node starting at a leaf
+    BotSort::TempStorage* tmp = (BotSort::TempStorage*)((((uintptr_t)(nrank + BOT_LEAVES)) + 15) & ~(uintptr_t)15);
+    __shared__ u32 wtot[4];
+
+    const int tid = threadIdx.x;
+    const i64 leaf0 = (i64)blockIdx.x * BOT_LEAVES;
+    const i64 p0 = leaf0 * LEAF;
+    const int nl = (int)min((i64)BOT_LEAVES, n_leaves - leaf0);        // leaves of this block
+    const int np = (int)min((i64)BOT_POINTS, n - p0);                  // real points of this block
+    for (int s = tid; s < BOT_POINTS; s += BOT_THREADS) {
+        u32 id = 0xffffffffu;
+        if (s < np) {
+            id = perm[p0 + s];
+            const T* row = P + (i64)id * d;
+            for (int j = 0; j < d; j++) coords[(size_t)j * BOT_POINTS + s] = (float)row[j];
+        }
+        ids[s] = id;
+        order[s] = (u32)s;
+    }
+    for (int l = tid; l < BOT_LEAVES; l += BOT_THREADS) { nA[l] = 0; nB[l] = (u32)nl; }
+    __syncthreads();
+    auto dec = [](u32 o) { u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; return __uint_as_float(b); };
+    for (int level = 0; level < 8; level++) {
+        // any node left with more than one leaf?
+        int active = 0;
+        for (int l = tid; l < nl; l += BOT_THREADS) active |= (nB[l] - nA[l] > 1) ? 1 : 0;
+        if (!__syncthreads_or(active)) break;
+        for (int e = tid; e < BOT_LEAVES * d; e += BOT_THREADS) { blo[e] = 0xffffffffu; bhi[e] = 0u; }
+        __syncthreads();
+        // tight boxes of the nodes being split: a warp covers one leaf per step, reduces, then one atomic per axis
+        for (int s = tid; s < BOT_POINTS; s += BOT_THREADS) {
+            const int leaf = s >> 5;
+            if (leaf >= nl) break;
+            const u32 a = nA[leaf];
+            if (nB[leaf] - a > 1) {
+                const bool valid = s < np;
+                const u32 pt = order[s];
+                for (int j = 0; j < d; j++) {
+                    const u32 o = valid ? f32_to_ordered(coords[(size_t)j * BOT_POINTS + pt]) : 0u;
+                    const u32 mn = __reduce_min_sync(0xffffffffu, valid ? o : 0xffffffffu);
+                    const u32 mx = __reduce_max_sync(0xffffffffu, o);
+                    if ((tid & 31) == 0) {
+                        atomicMin(&blo[a * d + j], mn);
+                        atomicMax(&bhi[a * d + j], mx);
+                    }
+                }
+            }
+        }
+        // nodes are numbered in order so the sort key needs only log2(#nodes) node bits
+        if (tid < BOT_LEAVES) {
+            const bool head = tid < nl && nA[tid] == (u32)tid;
+            const u32 bal = __ballot_sync(0xffffffffu, head);
+            nrank[tid] = __popc(bal & ((1u << (tid & 31)) - 1u));
+            if ((tid & 31) == 0) wtot[tid >> 5] = __popc(bal);
+        }
+        __syncthreads();
+        u32 n_nodes = 0;
+        for (int w = 0; w < BOT_LEAVES / 32; w++) {
+            if (tid < BOT_LEAVES && w < (tid >> 5)) nrank[tid] += wtot[w];
+            n_nodes += wtot[w];
+        }
+        const int nbits = n_nodes > 1 ? 32 - __clz(n_nodes - 1) : 0;
+        for (int l = tid; l < nl; l += BOT_THREADS) {
+            if (nA[l] == (u32)l && nB[l] - nA[l] > 1) {
+                int dim = 0;
+                float best = -1.f, lo_ = 0.f, ext_ = 0.f;
+                for (int j = 0; j < d; j++) {
+                    const float lo = dec(blo[l * d + j]), hi = dec(bhi[l * d + j]);
+                    float ext = hi - lo;
+                    ext = ext > 0.f ? ext : 0.f;
+                    if (ext > best) { best = ext; dim = j; lo_ = lo; ext_ = ext; }
+                }
+                sdim[l] = dim;
+                slo[l] = lo_;
+                ssc[l] = ext_ > 0.f ? (float)((1u << cb) - 1u) / ext_ : 0.f;
+            }
+        }
+        __syncthreads();
+        // keys (blocked arrangement: thread t owns slots t*ITEMS .. t*ITEMS+ITEMS-1), sort, new order
+        u32 keys[BOT_ITEMS], vals[BOT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < BOT_ITEMS; k++) {
+            const int s = tid * BOT_ITEMS + k;
+            u32 key = 0xffffffffu;
+            u32 pt = order[s];
+            if (s < np) {
+                const int leaf = s >> 5;
+                const u32 a = nA[leaf];
+                u32 low;
+                if (nB[leaf] - a > 1) {
+                    const float top = (float)((1u << cb) - 1u);
+                    float qf = (coords[(size_t)sdim[a] * BOT_POINTS + pt] - slo[a]) * ssc[a];
+                    qf = qf < 0.f ? 0.f : (qf > top ? top : qf);
+                    low = (u32)qf;
+                } else {
+                    low = (u32)(s & 31);
+                }
+                key = (nrank[a] << cb) | low;
+            }
+            keys[k] = key;                        // padding slots (all ones) stay last: the sort is stable
+            vals[k] = pt;
+        }
+        __syncthreads();
+        BotSort(*tmp).Sort(keys, vals, 0, cb + nbits);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BOT_ITEMS; k++) order[tid * BOT_ITEMS + k] = vals[k];
+        for (int l = tid; l < nl; l += BOT_THREADS) {
+            u32 a = nA[l], b = nB[l];
+            if (b - a > 1) {
+                const u32 mid = split_mid(a + (u32)leaf0, b + (u32)leaf0) - (u32)leaf0;   // aligned in GLOBAL leaf indices
+                if ((u32)l < mid) b = mid; else a = mid;
+                nA[l] = a;
+                nB[l] = b;
+            }
+        }
+        __syncthreads();
+    }
+    for (int s = tid; s < np; s += BOT_THREADS) perm[p0 + s] = ids[order[s]];
+}
+
 // one warp per leaf: gather the leaf's points into its tile
 template <typename T>
 __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restrict__ P, u32* perm, char* tiles,
@@ -356,13 +509,17 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     // order can serve several cuts (quantile slabs).  Measured on B200: in <= 3-D three levels per sort are
     // best throughout; in higher dimensions slabs cost search time near the leaves, so the upper levels take
     // two per sort and the last 7 levels (128-leaf subtrees) one each.  AL_TREE_LEVELS / AL_TREE_TOP override.
+    // The last 7 levels (subtrees of 128 leaves) are finished in shared memory by tree_bottom_kernel when a
+    // block's coordinates fit (d <= 9); the global rounds then only go down to 128-leaf nodes.
+    const bool use_bottom = tree_bottom_smem(d) <= 220 * 1024 && getenv("AL_TREE_NO_BOTTOM") == nullptr;
     int top_levels = d <= 3 ? 3 : 2;
     int top_rounds = d <= 3 ? 64 : (depth > 7 ? (depth - 7) / 2 : 0);
+    const int global_depth = use_bottom ? (depth > 7 ? depth - 7 : 0) : depth;
     if (const char* e = getenv("AL_TREE_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 8) top_levels = v; }
     if (const char* e = getenv("AL_TREE_TOP")) { int v = atoi(e); if (v >= 0 && v <= 64) top_rounds = v; }
     int sched[64];
     int rounds = 0;
-    for (int done = 0; done < depth && rounds < 64; rounds++) {
+    for (int done = 0; done < global_depth && rounds < 64; rounds++) {
         sched[rounds] = rounds < top_rounds ? top_levels : 1;
         done += sched[rounds];
     }
@@ -393,6 +550,14 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
         AL_CHECK_LAUNCH();
     }
     if (vals[cur] != perm) AL_CUDA(cudaMemcpyAsync(perm, vals[cur], sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+    if (use_bottom && depth > 0) {
+        const size_t smem = tree_bottom_smem(d);
+        AL_CUDA(cudaFuncSetAttribute(tree_bottom_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int cb = 10;      // coordinate bits of the in-block sort key: children overlap by at most 1/1024 of the node extent
+        if (const char* e = getenv("AL_TREE_BOT_CBITS")) { int v = atoi(e); if (v >= 5 && v <= 16) cb = v; }   // development knob
+        tree_bottom_kernel<T><<<(unsigned)((n_leaves + BOT_LEAVES - 1) / BOT_LEAVES), BOT_THREADS, smem, st>>>(P, perm, n, n_leaves, d, cb);
+        AL_CHECK_LAUNCH();
+    }
 
     const int eb = (int)sizeof(T);
     T* lo0 = (T*)(base + h.box_off[0]);
