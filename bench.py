@@ -176,9 +176,14 @@ def run_reference(args):
     oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
     P, kwargs, desc = make_workload(args.workload)
     n_s = min(args.cpu_sample, P.shape[0])
-    sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
+    # warm-up on a small prefix; its rate sizes the per-step sample so that K steps stay within about three minutes
+    n_w = max(20000, n_s // 20)
+    t_w = 0.0
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_hot_path_seconds(sample[: max(20000, n_s // 20)], kwargs)
+        t_w, _ = cpu_hot_path_seconds(np.ascontiguousarray(P[:n_w]), kwargs)
+    if t_w > 0:
+        n_s = int(max(min(n_s, 200000), min(n_s, 180.0 / max(1, args.steps) * (n_w / t_w))))
+    sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
     times = []
     stage = None
     for _ in range(args.steps):
@@ -351,7 +356,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
-    oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
+        oracle.set_num_threads()      # all host cores regardless of OMP_NUM_THREADS
         n_s = min(args.cpu_sample, n)
         sample = np.ascontiguousarray(P[:n_s])
         cpu_hot_path_seconds(sample[:20000], kwargs)
