@@ -17,6 +17,11 @@ __global__ void agg_fill_kernel(u32* p, u32 v, i64 n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
 }
 
+__global__ void agg_save_last_kernel(const u32* last_in, u32* tot) { tot[0] = *last_in; }
+__global__ void agg_total_kernel(const u32* last_out, u32* tot) { tot[1] = *last_out + tot[0]; }
+
+// Everything runs on one stream, so workspace released with ar.reset() may be handed to the next
+// kernel without a host synchronisation: stream order already separates the two uses.
 struct CudaExec {
     cudaStream_t st;
     cudaError_t err = cudaSuccess;
@@ -57,11 +62,17 @@ struct CudaExec {
         note(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, st));
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return -1; }
-        u32 last_in = read_u32(in + (n - 1));      // read before the scan: `out` may alias later users of `in`
+        u32* tot = ar.get<u32>(2);
+        if (!ar.ok) { ar.reset(mk); return -1; }
+        // the last input is saved before the scan (`out` may alias `in`); one device-side add, one host read
+        agg_save_last_kernel<<<1, 1, 0, st>>>(in + (n - 1), tot);
         note(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, st));
-        u32 last_out = read_u32(out + (n - 1));
+        agg_total_kernel<<<1, 1, 0, st>>>(out + (n - 1), tot);
+        note(cudaGetLastError());
+        launches += 2;
+        const u32 total = read_u32(tot + 1);
         ar.reset(mk);
-        return (i64)last_out + (i64)last_in;
+        return (i64)total;
     }
     void inclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar) {
         if (n <= 0) return;
@@ -71,7 +82,6 @@ struct CudaExec {
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceScan::InclusiveSum(tmp, tb, in, out, n, st));
-        note(cudaStreamSynchronize(st));   // tmp is released below
         ar.reset(mk);
     }
     void sort_pairs_u64_u32(const u64* k_in, u64* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena& ar) {
@@ -82,7 +92,6 @@ struct CudaExec {
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
-        note(cudaStreamSynchronize(st));
         ar.reset(mk);
     }
     void sort_pairs_u32_u32(const u32* k_in, u32* k_out, const u32* v_in, u32* v_out, i64 n, int end_bit, AggArena& ar) {
@@ -95,10 +104,9 @@ struct CudaExec {
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceRadixSort::SortPairs(tmp, tb, k_in, k_out, v_in, v_out, n, 0, end_bit, st));
-        note(cudaStreamSynchronize(st));
         ar.reset(mk);
     }
-    void sync() { note(cudaStreamSynchronize(st)); }
+    void sync() {}      // stream order is enough between the passes (see above); hosts that need results call read_u32
     void segmented_inclusive_scan(SegItem* items, i64 n, AggArena& ar) {
         if (n <= 0) return;
         const size_t mk = ar.mark();
@@ -107,7 +115,6 @@ struct CudaExec {
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceScan::InclusiveScan(tmp, tb, items, items, SegOp(), n, st));
-        note(cudaStreamSynchronize(st));
         ar.reset(mk);
     }
     char lvl_name[64];
@@ -158,6 +165,7 @@ extern "C" int al_aggregate(const void* logrho, int dtype, const uint32_t* sorte
     else
         rc = agg::run<CudaExec, double>(x, ar, (const double*)logrho, sorted_pairs, n, E, true, ordering_out, groups_out,
                                         (double*)prominences_out, n_groups_host);
+    x.note(cudaStreamSynchronize(x.st));     // surfaces asynchronous kernel errors in this call's return code
     al_count_launches(x.launches);
     if (x.err != cudaSuccess) {
         al_set_error("al_aggregate: CUDA error: %s", cudaGetErrorString(x.err));

@@ -170,12 +170,20 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         // pointer jumping to the component roots
         for (int it = 0; it < 64; it++) {
             x.fill_u32(changed, 0, 1);
-            for (int rep = 0; rep < 3; rep++)
-                x.template launch<TagJump>(N, AGG_LAMBDA(i64 s) {
-                    u32 h = hook[s];
-                    u32 hh = hook[h];
-                    if (hh != h) { hook[s] = hh; *changed = 1; }
-                });
+            // every vertex chases its pointer a bounded number of hops and stores where it got to; concurrent
+            // stores only ever replace a pointer by an ancestor, so stale reads are safe
+            x.template launch<TagJump>(N, AGG_LAMBDA(i64 s) {
+                u32 h = hook[s];
+                const u32 h0 = h;
+                bool at_root = false;
+                for (int hop = 0; hop < 24; hop++) {
+                    const u32 hh = hook[h];
+                    if (hh == h) { at_root = true; break; }
+                    h = hh;
+                }
+                if (h != h0) hook[s] = h;
+                if (!at_root) *changed = 1;
+            });
             if (x.read_u32(changed) == 0) break;
         }
         x.template launch<TagRoots>(N, AGG_LAMBDA(i64 s) { flag[s] = hook[s] == (u32)s ? 1u : 0u; });
