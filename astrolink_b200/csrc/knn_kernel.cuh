@@ -360,8 +360,10 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     typedef typename KS::Key Key;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const i64 ql = p.leaf_begin + (i64)blockIdx.x * WARPS + wib;
-    if (ql >= p.leaf_end) return;
+    // leaf and node indices fit 32 bits (n < 2^31, 32-point leaves): the traversal uses int arithmetic
+    const i64 ql64 = p.leaf_begin + (i64)blockIdx.x * WARPS + wib;
+    if (ql64 >= p.leaf_end) return;
+    const int ql = (int)ql64;
     const int K = p.k;
 
     // ---- per-warp shared memory carve-up (integer offsets from the shared base)
@@ -376,8 +378,8 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     o += (size_t)K * 32 * KS::BYTES;
     T* qtab = (T*)o;                                        // [32][RS]: query coordinates, k-th distance
     u32* sneed = (u32*)(qtab + 32 * RS);                    // [n_levels + 1][32] per-child query masks
-    i64* snode = (i64*)(sneed + (p.n_levels + 1) * 32);     // [MAX_WIDE_LEVELS]
-    u32* smask = (u32*)(snode + MAX_WIDE_LEVELS);           // [MAX_WIDE_LEVELS]
+    int* snode = (int*)(sneed + (p.n_levels + 1) * 32);     // [MAX_WIDE_LEVELS] (8 bytes reserved per entry)
+    u32* smask = (u32*)(snode + 2 * MAX_WIDE_LEVELS);       // [MAX_WIDE_LEVELS]
     int* slevel = (int*)(smask + MAX_WIDE_LEVELS);          // [MAX_WIDE_LEVELS]
     u64* bars = (u64*)(slevel + MAX_WIDE_LEVELS);           // [2]
     const u32 tile_sa = smem_u32(wbase);                    // shared address of tile buffer 0
@@ -408,12 +410,13 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     // the query box: tight bounds of the own leaf (level-0 box arrays)
     T qlo[D], qhi[D];
     {
+        const int cnt0 = (int)p.count[0];
         const T* lo0 = (const T*)p.box[0];
-        const T* hi0 = lo0 + (i64)D * p.count[0];
+        const T* hi0 = lo0 + (i64)D * cnt0;
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            qlo[j] = lo0[(i64)j * p.count[0] + ql];
-            qhi[j] = hi0[(i64)j * p.count[0] + ql];
+            qlo[j] = lo0[j * cnt0 + ql];
+            qhi[j] = hi0[j * cnt0 + ql];
             s.q[j] = (T)0;
         }
     }
@@ -423,9 +426,9 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     // for every query in `qmask` the distance from the query to the child's box against the query's own
     // k-th distance.  Returns the children some query needs; per-child query masks go to need_out[lane].
     u32 top_dist = 0xffffffffu;     // this lane's child-box distance (float bits) of the most recent open
-    auto open_node = [&](int hc, i64 node, i64 excl, u32 qmask, u32* need_out) -> u32 {
-        const i64 cnt = p.count[hc];
-        const i64 c = node * FANOUT + lane;
+    auto open_node = [&](int hc, int node, int excl, u32 qmask, u32* need_out) -> u32 {
+        const int cnt = (int)p.count[hc];
+        const int c = node * FANOUT + lane;
         const bool ok = c < cnt && c != excl;
         const T* lo = (const T*)p.box[hc];
         const T* hi_ = lo + (i64)D * cnt;
@@ -433,8 +436,8 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         T acc = (T)0;
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            blo[j] = ok ? lo[(i64)j * cnt + c] : (T)0;
-            bhi[j] = ok ? hi_[(i64)j * cnt + c] : (T)0;
+            blo[j] = ok ? lo[j * cnt + c] : (T)0;        // D * cnt < 2^31
+            bhi[j] = ok ? hi_[j * cnt + c] : (T)0;
             T a = blo[j] - qhi[j], b = qlo[j] - bhi[j];
             const T g = gap_t(a, b);
             acc = fma_t<T>(g, g, acc);
@@ -471,17 +474,17 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     int anc = 0;    // 0: own leaf not yet emitted; g >= 1: next ancestor level to open
     int sp = 0;     // entries on the stack, including the register-resident top
     u32 t_mask = 0;
-    i64 t_node = 0;
+    int t_node = 0;
     int t_h = 0;
     u32 cand_need = FULL;
-    auto next_candidate = [&]() -> i64 {
+    auto next_candidate = [&]() -> int {
         if (anc == 0) { anc = 1; cand_need = FULL; return ql; }
         for (;;) {
             if (sp == 0) {
                 if (anc > p.n_levels) return -1;
                 // open the children of the level-`anc` ancestor, except the branch already done
                 if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
-                const i64 node = ql >> (5 * anc), excl = ql >> (5 * (anc - 1));
+                const int node = ql >> (5 * anc), excl = ql >> (5 * (anc - 1));
                 t_mask = open_node(anc - 1, node, excl, FULL, sneed);
                 t_node = node;
                 t_h = anc;
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             }
             t_mask &= ~(1u << bit);
             const u32 need = sneed[(sp - 1) * 32 + bit];
-            const i64 c = t_node * FANOUT + bit;
+            const int c = t_node * FANOUT + bit;
             if (t_h == 1) { cand_need = need; return c; }
             // descend: save the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
             if (lane == 0) { smask[sp - 1] = t_mask; snode[sp - 1] = t_node; slevel[sp - 1] = t_h; }
@@ -536,19 +539,19 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     };
 
     u32 phase = 0;
-    i64 pending = -1;
+    int pending = -1;
     u32 pending_need = 0;
     int bi = 0;                 // buffer the next issue goes to
     for (;;) {
         // no look-ahead while the own leaf is pending: box tests need the queries and their first bounds
         const bool lookahead = pending != ql;
-        const i64 cand = lookahead ? next_candidate() : -1;
+        const int cand = lookahead ? next_candidate() : -1;
         const u32 cneed = cand_need;
         if (cand >= 0) {
             __syncwarp();       // every lane is done reading buffer bi
             if (lane == 0) {
                 mbar_expect_tx(&bars[bi], (u32)p.tile_stride);
-                tma_load_1d(wbase + (u32)bi * (u32)p.tile_stride, p.tiles + cand * (i64)p.tile_stride, (u32)p.tile_stride,
+                tma_load_1d(wbase + (u32)bi * (u32)p.tile_stride, p.tiles + (size_t)(u32)cand * (u32)p.tile_stride, (u32)p.tile_stride,
                             &bars[bi]);
             }
             n_loaded++;
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         hk.st(m * 32 + lane, hk.ld(lane));
         heap_replace_root<T>(hk, m, lane, t);
     }
-    const i64 pos_row = (ql - p.leaf_begin) * LEAF + lane;
+    const i64 pos_row = (ql64 - p.leaf_begin) * LEAF + lane;
     if (s.active) {
         const i64 row = p.row_order == 0 ? (i64)my_id : pos_row;
         u32* io = p.idx_out + row * K;
