@@ -150,13 +150,15 @@ class Index:
         """index position -> original point (uint32 viewed as int32 tensor; padding = -1)."""
         return self.buf[256:256 + 4 * self.positions].view(torch.int32)
 
-    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None):
+    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None, want_idx=True):
         """a3: exact kNN of the points at index positions [pos_begin, pos_end).  link_out: optional
-        [n, L] int32 tensor (possibly peer-mapped) that receives the L nearest ids at the original row."""
+        [n, L] int32 tensor (possibly peer-mapped) that receives the L nearest ids at the original row;
+        with want_idx=False (link_out required) the full [rows, k] index array is not written (idx is None)."""
         L = lib()
         pos_end = self.positions if pos_end is None else pos_end
         rows = self.n if row_order == 0 else pos_end - pos_begin
-        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        assert want_idx or link_out is not None
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device) if want_idx else None
         d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
         pairs = torch.zeros(8, dtype=torch.int64, device=self.device) if count_pairs else None
         ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)

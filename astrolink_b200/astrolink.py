@@ -269,18 +269,21 @@ class AstroLink:
             if world == 1:
                 a, b = self._stage("knn")
                 a.record()
-                d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True)
+                # the k_link nearest ids go straight to their own [n, k_link] array (astrolink.py:286) from the
+                # search kernel's epilogue; the full index rows are only written when the weights need them
+                kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
+                d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=w is not None)
                 b.record()
                 a, b = self._stage("density")
                 a.record()
                 raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
-                kNN = idx[:, :L].contiguous() if L < K else idx
-                del d2
+                b.record()
+                del d2, idx
             else:
                 raw, kNN = self._sharded_knn(index, w, rank, world)
-                a, b = self._stage("density")
-                a.record()
             # with the peer exchange only rank 0 holds the densities (results live on rank 0)
+            a, b = self._stage("normalise")
+            a.record()
             lr = nat.normalise_(raw) if (world == 1 or rank == 0 or getattr(self._dist, "peer", None) is None) else raw
             b.record()
             self._set_dev("logRho", lr)
@@ -389,27 +392,34 @@ class AstroLink:
     def _fetch_results(self):
         side = torch.cuda.Stream(device=self._device)
         side.wait_stream(torch.cuda.current_stream())
-        bufs = {}
+        bufs, done = {}, {}
         with torch.cuda.stream(side):
+            # small results first: the fit only waits for them, the large copies run underneath it
             for name in ("groups", "prominences", "ordering", "logRho"):
                 d = self.__dict__["_d_" + name]
                 h = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
                 h.copy_(d, non_blocking=True)
                 bufs[name] = h
-        self._pending = (side, bufs)
+                done[name] = torch.cuda.Event()
+                done[name].record(side)
+        self._pending = (side, bufs, done)
 
-    def _finish_fetch(self, names):
+    def _finish_fetch(self, names=None):
+        """Waits for the device-to-host copies of `names` (None: all that are still pending)."""
         pend = self.__dict__.get("_pending")
         if pend is None:
             return
-        side, bufs = pend
-        side.synchronize()
+        side, bufs, done = pend
         for name in list(bufs):
+            if names is not None and name not in names:
+                continue
+            done.pop(name).synchronize()
             h = bufs.pop(name).numpy()
             if name in ("groups", "ordering"):
                 h = h.view(np.uint32)
             self.__dict__["_h_" + name] = h
-        self._pending = None
+        if not bufs:
+            self._pending = None
 
     # ------------------------------------------------------------------ host statistics
     def compute_significances(self):
@@ -441,7 +451,7 @@ class AstroLink:
         if self.verbose > 1:
             self._printFunction('Finding clusters...       ')
         start = time.perf_counter()
-        self._finish_fetch(())
+        self._finish_fetch()
         if self.S == 'auto':
             self.S = stats.auto_threshold(self.prominences.shape[0])
         self.clusters, self.ids, self.significances = stats.extract(self.groups, self.groups_sigs, self.S, self.h_style,

@@ -31,6 +31,8 @@ extern "C" int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end
                            size_t ws_bytes, void* stream) {
     (void)ws; (void)ws_bytes;
     AL_REQUIRE(link_out == nullptr || (link_cols >= 1 && link_cols <= k), AL_EINVAL, "al_knn_link: link_cols must be in [1, k]");
+    AL_REQUIRE(d2_out != nullptr, AL_EINVAL, "al_knn: d2_out is NULL");
+    AL_REQUIRE(idx_out != nullptr || link_out != nullptr, AL_EINVAL, "al_knn: idx_out may only be NULL when link_out is given");
     IndexHeader h;
     if (!index_lookup(index, &h)) {
         AL_CUDA(cudaMemcpy(&h, index, sizeof(h), cudaMemcpyDeviceToHost));

@@ -657,17 +657,20 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     const i64 pos_row = (ql64 - p.leaf_begin) * LEAF + lane;
     if (s.active) {
         const i64 row = p.row_order == 0 ? (i64)my_id : pos_row;
-        u32* io = p.idx_out + row * K;
         T* dd = (T*)p.d2_out + row * K;
 #pragma unroll 1
-        for (int m = 0; m < K; m++) {
-            const Key t = hk.ld(m * 32 + lane);
-            io[m] = KS::id(t);
-            dd[m] = KS::dist(t);
+        for (int m = 0; m < K; m++) dd[m] = KS::dist(hk.ld(m * 32 + lane));
+        if (p.idx_out != nullptr) {      // optional: callers that only need the link columns pass NULL
+            u32* io = p.idx_out + row * K;
+#pragma unroll 1
+            for (int m = 0; m < K; m++) io[m] = KS::id(hk.ld(m * 32 + lane));
         }
     } else if (p.row_order == 1) {
 #pragma unroll 1
-        for (int m = 0; m < K; m++) { p.idx_out[pos_row * K + m] = 0xffffffffu; ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>(); }
+        for (int m = 0; m < K; m++) {
+            if (p.idx_out != nullptr) p.idx_out[pos_row * K + m] = 0xffffffffu;
+            ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>();
+        }
     }
     if (p.link_out != nullptr && s.active) {
         // the exchange step of the multi-GPU path, fused into the epilogue: the k_link nearest ids go

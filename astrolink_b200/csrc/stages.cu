@@ -320,18 +320,86 @@ __global__ void __launch_bounds__(256) make_edges_kernel(const T* __restrict__ l
     }
 }
 
+// Same edges, memory traffic reshaped for HBM: a block of 256 points reads its 256 x L neighbour ids as one
+// contiguous run (coalesced), every thread gathers the L densities of its row (the 4 n bytes of logRho stay in
+// L2), builds its L-1 edges in shared memory, and the block's 256 (L-1) edges -- contiguous in the output --
+// leave with fully coalesced stores.  Every point emits exactly L-1 edges (its row holds itself once, or --
+// rows of coincident duplicates, App. B Q7 -- the last entry is dropped).
+constexpr int ME_BLOCK = 256;
+template <typename T>
+static size_t make_edges_smem_bytes(int L) { return (size_t)ME_BLOCK * ((size_t)L * 4 + (size_t)(L - 1) * (sizeof(T) + 8)); }
+
+template <typename T>
+__global__ void __launch_bounds__(ME_BLOCK) make_edges_staged_kernel(const T* __restrict__ logrho, const u32* __restrict__ knn,
+                                                                     i64 knn_stride, i64 n, int L, T* __restrict__ w_out,
+                                                                     uint2* __restrict__ pairs_out) {
+    extern __shared__ __align__(16) unsigned char me_smem[];
+    const int E1 = L - 1;
+    uint2* s_pairs = (uint2*)me_smem;                                  // [ME_BLOCK * (L-1)]
+    T* s_w = (T*)(s_pairs + (size_t)ME_BLOCK * E1);                    // [ME_BLOCK * (L-1)]
+    u32* s_knn = (u32*)(s_w + (size_t)ME_BLOCK * E1);                  // [ME_BLOCK * L]
+    const i64 b0 = (i64)blockIdx.x * ME_BLOCK;
+    const int rows = (int)((n - b0) < ME_BLOCK ? (n - b0) : ME_BLOCK);
+    const int t = threadIdx.x;
+    if (knn_stride == L) {
+        const u32* src = knn + b0 * L;
+        for (int e = t; e < rows * L; e += ME_BLOCK) s_knn[e] = src[e];
+    } else {
+        for (int e = t; e < rows * L; e += ME_BLOCK) s_knn[e] = knn[(b0 + e / L) * knn_stride + e % L];
+    }
+    __syncthreads();
+    if (t < rows) {
+        const i64 i = b0 + t;
+        const T li = logrho[i];
+        const u32* row = s_knn + t * L;
+        int o = t * E1;
+        const int oend = o + E1;
+        for (int r0 = 0; r0 < L; r0 += ME_CHUNK) {
+            u32 j[ME_CHUNK];
+            T lj[ME_CHUNK];
+#pragma unroll
+            for (int e = 0; e < ME_CHUNK; e++) j[e] = r0 + e < L ? row[r0 + e] : (u32)i;
+#pragma unroll
+            for (int e = 0; e < ME_CHUNK; e++) lj[e] = logrho[j[e]];                            // all the gathers in flight
+#pragma unroll
+            for (int e = 0; e < ME_CHUNK; e++) {
+                if ((i64)j[e] == i || o >= oend) continue;
+                if (li >= lj[e]) { s_w[o] = lj[e]; s_pairs[o] = make_uint2((u32)i, j[e]); }
+                else { s_w[o] = li; s_pairs[o] = make_uint2(j[e], (u32)i); }
+                o++;
+            }
+        }
+    }
+    __syncthreads();
+    const i64 pos0 = b0 * E1;
+    const int cnt = rows * E1;
+    for (int e = t; e < cnt; e += ME_BLOCK) w_out[pos0 + e] = s_w[e];
+    for (int e = t; e < cnt; e += ME_BLOCK) pairs_out[pos0 + e] = s_pairs[e];
+}
+
+template <typename T>
+static int make_edges_launch(const T* logrho, const u32* knn, i64 knn_stride, i64 n, int L, T* w_out, uint2* pairs_out, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + ME_BLOCK - 1) / ME_BLOCK);
+    const size_t smem = make_edges_smem_bytes<T>(L);
+    if (smem <= 160 * 1024) {
+        if (smem > 48 * 1024)
+            AL_CUDA(cudaFuncSetAttribute(make_edges_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        make_edges_staged_kernel<T><<<grid, ME_BLOCK, smem, st>>>(logrho, knn, knn_stride, n, L, w_out, pairs_out);
+    } else {
+        make_edges_kernel<T><<<grid, 256, 0, st>>>(logrho, knn, knn_stride, n, L, w_out, pairs_out);      // very long rows
+    }
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+
 extern "C" int al_make_edges(const void* logrho, int dtype, const uint32_t* knn, int64_t knn_stride, int64_t n, int L,
                              void* weights_out, uint32_t* pairs_out, void* stream) {
     AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_make_edges: bad dtype");
     AL_REQUIRE(n >= 1 && L >= 2 && knn_stride >= L, AL_EINVAL, "al_make_edges: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned grid = (unsigned)((n + 255) / 256);
     if (dtype == AL_F32)
-        make_edges_kernel<float><<<grid, 256, 0, st>>>((const float*)logrho, knn, knn_stride, n, L, (float*)weights_out, (uint2*)pairs_out);
-    else
-        make_edges_kernel<double><<<grid, 256, 0, st>>>((const double*)logrho, knn, knn_stride, n, L, (double*)weights_out, (uint2*)pairs_out);
-    AL_CHECK_LAUNCH();
-    return AL_OK;
+        return make_edges_launch<float>((const float*)logrho, knn, knn_stride, n, L, (float*)weights_out, (uint2*)pairs_out, st);
+    return make_edges_launch<double>((const double*)logrho, knn, knn_stride, n, L, (double*)weights_out, (uint2*)pairs_out, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -321,7 +321,8 @@ def run_b200(args):
     E = n * (L - 1)
     esz = 4
     hbm = {   # algorithmic bytes per launch (DESIGN.md "Kernels")
-        "density": n * K * esz + n * esz + 3 * n * esz,
+        "density": n * K * esz + n * esz,
+        "normalise": 3 * n * esz,
         "edges": n * L * 4 + n * L * esz + n * esz + E * (esz + 8),
         "sort": E * 4 + E * 68 + E * 16,
     }

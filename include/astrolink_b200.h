@@ -87,7 +87,8 @@ int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row
 
 /* a3 with the multi-GPU exchange fused in: additionally writes the first `link_cols` neighbour ids of every
  * query to link_out[original index][link_cols].  link_out may be a peer-mapped pointer into another GPU's
- * memory (NVLink): the rows then land directly in the consumer's kNN buffer and no all-gather is needed. */
+ * memory (NVLink): the rows then land directly in the consumer's kNN buffer and no all-gather is needed.
+ * idx_out may be NULL when link_out is given (callers that only keep the k_link columns, astrolink.py:286). */
 int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out, void* d2_out,
                 uint32_t* link_out, int link_cols, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
 
