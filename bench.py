@@ -203,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -365,14 +365,32 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                                 "sample": f"{n_s}-point prefix of the shuffled workload, one run ({sec:.1f} s); oracle C port "
                                           f"(OpenMP KD-tree kNN, serial aggregate) + Python host stats"}
-    print(json.dumps(line))
+    _emit(line)
     if D is not None:
         import torch.distributed as td
         td.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """The one JSON line goes to the process's original stdout; everything else printed while the
+    benchmark runs (NCCL's version banner, library chatter) was diverted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)              # fd 1 -> stderr for the duration of the run
     args = parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
