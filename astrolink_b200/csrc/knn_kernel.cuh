@@ -39,7 +39,10 @@
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 5
 #endif
-constexpr int WARPS = 4;             // warps (query leaves) per CTA
+#ifndef KNN_WARPS
+#define KNN_WARPS 4
+#endif
+constexpr int WARPS = KNN_WARPS;     // warps (query leaves) per CTA
 constexpr int QCAP = KNN_QCAP;       // queue entries per lane
 #ifndef KNN_CHUNK_PB
 #define KNN_CHUNK_PB 2
