@@ -48,6 +48,9 @@ _SIGS = {
     "al_peer_open": (_int, [_vp, _vp]),
     "al_peer_release": (_int, [_vp, _int]),
     "al_knn_link": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
+    "al_knn_dealt": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
+    "al_knn_dealt_rows": (_i64, [_i64, _i64, _i64, _i64]),
+    "al_logrho_dealt": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _i64, _i64, _i64, _i64, _vp, _vp]),
     "al_logrho_rows": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _vp, _vp, _vp]),
     "al_enable_peer_access": (_int, [_int]),
     "al_w1_workspace_bytes": (_sz, [_i64]),
@@ -150,21 +153,25 @@ class Index:
         """index position -> original point (uint32 viewed as int32 tensor; padding = -1)."""
         return self.buf[256:256 + 4 * self.positions].view(torch.int32)
 
-    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None, want_idx=True):
+    def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None, want_idx=True,
+            chunk=0, stride=0):
         """a3: exact kNN of the points at index positions [pos_begin, pos_end).  link_out: optional
         [n, L] int32 tensor (possibly peer-mapped) that receives the L nearest ids at the original row;
-        with want_idx=False (link_out required) the full [rows, k] index array is not written (idx is None)."""
+        with want_idx=False (link_out required) the full [rows, k] index array is not written (idx is None).
+        chunk/stride (positions): search the dealt chunks [pos_begin + c*stride, +chunk) below pos_end
+        (al_knn_dealt; row_order must be 1, rows in launch order)."""
         L = lib()
         pos_end = self.positions if pos_end is None else pos_end
-        rows = self.n if row_order == 0 else pos_end - pos_begin
+        rows = self.n if row_order == 0 else int(L.al_knn_dealt_rows(pos_begin, pos_end, chunk, stride))
         assert want_idx or link_out is not None
         idx = torch.empty((rows, k), dtype=torch.int32, device=self.device) if want_idx else None
         d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
         pairs = torch.zeros(8, dtype=torch.int64, device=self.device) if count_pairs else None
         ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)
         link_cols = 0 if link_out is None else int(link_out.shape[1])
-        _check(L.al_knn_link(_ptr(self.buf), pos_begin, pos_end, k, row_order, _ptr(idx), _ptr(d2), _ptr(link_out), link_cols,
-                             _ptr(pairs), _ptr(ws), ws.numel(), _stream()), "al_knn_link")
+        if rows > 0:
+            _check(L.al_knn_dealt(_ptr(self.buf), pos_begin, pos_end, chunk, stride, k, row_order, _ptr(idx), _ptr(d2), _ptr(link_out),
+                                  link_cols, _ptr(pairs), _ptr(ws), ws.numel(), _stream()), "al_knn_dealt")
         if count_pairs:
             return d2, idx, pairs
         return d2, idx
@@ -182,6 +189,20 @@ def logrho(d2, idx, k_den, d_intrinsic, weights=None, row_ids=None, out=None):
         assert weights.dtype == torch.float64 and idx is not None and idx.is_contiguous()
     _check(L.al_logrho_rows(_ptr(d2), _ptr(idx), _ptr(weights), _dt(d2), nq, k, int(d_intrinsic), _ptr(row_ids), _ptr(out), _stream()),
            "al_logrho_rows")
+    return out
+
+
+def logrho_dealt(d2, idx, k_den, d_intrinsic, begin, end, chunk, stride, out, weights=None):
+    """a4/a5 for the rows of a dealt kNN launch, written at their index positions of `out` (possibly peer-mapped)."""
+    L = lib()
+    nq, k = d2.shape
+    assert k == k_den and d2.is_contiguous()
+    if nq == 0:
+        return out
+    if weights is not None:
+        assert weights.dtype == torch.float64 and idx is not None and idx.is_contiguous()
+    _check(L.al_logrho_dealt(_ptr(d2), _ptr(idx), _ptr(weights), _dt(d2), nq, k, int(d_intrinsic), begin, end, chunk, stride,
+                             _ptr(out), _stream()), "al_logrho_dealt")
     return out
 
 

@@ -332,14 +332,20 @@ class AstroLink:
         its density kernel the raw log-density, directly into rank 0's arrays (peer-mapped over NVLink)."""
         n, K, L = self.n_samples, self.k_den, self.k_link
         dt = torch.float32 if self.P.dtype == np.float32 else torch.float64
-        knn0 = peer.get("kNN", (n, L), torch.int32, self._device)
-        raw0 = peer.get("logRho_raw", (n,), dt, self._device)
+        from . import dist as adist
+        P_ = index.positions
+        half = peer.next_epoch()
+        knn0 = peer.get(f"kNN_by_position_{half}", (P_, L), torch.int32, self._device)
+        raw0 = peer.get(f"logRho_raw_by_position_{half}", (P_,), dt, self._device)
+        # The leaves are dealt to the ranks in chunks (evens out regional differences in search cost); every
+        # rank's rows go to rank 0 in index-position order, as full 128-byte stores from the kernels.
+        begin, chunk, stride, rows = adist.deal_chunks(P_, rank, self._world()[1], nat.LEAF)
         a, b = self._stage("knn")
         a.record()
-        d2, idx, self._knn_pairs = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1, count_pairs=True, link_out=knn0)
+        d2, idx, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True,
+                                             link_out=knn0, want_idx=w is not None, chunk=chunk, stride=stride)
         b.record()
-        row_ids = index.perm()[lo:hi]
-        nat.logrho(d2, idx, K, self.d_intrinsic, weights=w, row_ids=row_ids, out=raw0)
+        nat.logrho_dealt(d2, idx, K, self.d_intrinsic, begin, P_, chunk, stride, raw0, weights=w)
         del d2, idx
         a, b = self._stage("all_gather")
         a.record()
@@ -348,7 +354,16 @@ class AstroLink:
         b.record()
         if rank != 0:
             return torch.zeros((n,), dtype=dt, device=self._device), torch.zeros((1, L), dtype=torch.int32, device=self._device)
-        return raw0.tensor.clone(), knn0.tensor.clone()
+        # back to original point order (rank 0, local memory)
+        a, b = self._stage("unpermute")
+        a.record()
+        perm = index.perm()
+        kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
+        raw = torch.empty((n,), dtype=dt, device=self._device)
+        nat.scatter_rows(knn0.tensor, perm, kNN)
+        nat.scatter_rows(raw0.tensor.view(-1, 1), perm, raw.view(-1, 1))
+        b.record()
+        return raw, kNN
 
     # ------------------------------------------------------------------ a8-a11
     def aggregate(self):

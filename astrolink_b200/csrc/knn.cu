@@ -29,7 +29,26 @@ extern "C" int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int
 extern "C" int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out,
                            void* d2_out, uint32_t* link_out, int link_cols, unsigned long long* pairs_evaluated, void* ws,
                            size_t ws_bytes, void* stream) {
+    return al_knn_dealt(index, pos_begin, pos_end, 0, 0, k, row_order, idx_out, d2_out, link_out, link_cols, pairs_evaluated, ws,
+                        ws_bytes, stream);
+}
+
+extern "C" int64_t al_knn_dealt_rows(int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions) {
+    if (pos_end <= pos_begin) return 0;
+    if (chunk_positions <= 0) return pos_end - pos_begin;
+    return (pos_end - pos_begin + stride_positions - 1) / stride_positions * chunk_positions;
+}
+
+extern "C" int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                            int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
+                            unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream) {
     (void)ws; (void)ws_bytes;
+    AL_REQUIRE(chunk_positions >= 0 && (chunk_positions == 0 || (chunk_positions % (LEAF * WARPS) == 0 && stride_positions >= chunk_positions &&
+               stride_positions % chunk_positions == 0)), AL_EINVAL,
+               "al_knn_dealt: chunk_positions must be a multiple of %d and stride_positions a multiple of chunk_positions", LEAF * WARPS);
+    AL_REQUIRE(chunk_positions == 0 || row_order == 1, AL_EINVAL, "al_knn_dealt: dealt chunks need row_order 1");
+    // link rows: dealt launches (the sharded path) write them in index-position order, everything else by original index
+    const int link_by_position = chunk_positions > 0 ? 1 : 0;
     AL_REQUIRE(link_out == nullptr || (link_cols >= 1 && link_cols <= k), AL_EINVAL, "al_knn_link: link_cols must be in [1, k]");
     AL_REQUIRE(d2_out != nullptr, AL_EINVAL, "al_knn: d2_out is NULL");
     AL_REQUIRE(idx_out != nullptr || link_out != nullptr, AL_EINVAL, "al_knn: idx_out may only be NULL when link_out is given");
@@ -57,6 +76,8 @@ extern "C" int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end
     p.pair_block = h.pair_block;
     p.leaf_begin = pos_begin / LEAF;
     p.leaf_end = pos_end / LEAF;
+    p.chunk_blocks = chunk_positions / (LEAF * WARPS);
+    p.chunk_stride_blocks = stride_positions / (LEAF * WARPS);
     p.n = h.n;
     p.k = k;
     p.row_order = row_order;
@@ -64,6 +85,7 @@ extern "C" int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end
     p.d2_out = d2_out;
     p.link_out = link_out;
     p.link_cols = link_cols;
+    p.link_by_position = link_by_position;
     p.stats = pairs_evaluated;
     cudaStream_t st = (cudaStream_t)stream;
     if (h.dtype == AL_F32) {

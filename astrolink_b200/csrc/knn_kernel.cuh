@@ -60,6 +60,10 @@ struct KnnParams {
     int n_levels;
     int tile_stride, tile_hdr_bytes, tile_ids_off, pair_block;
     i64 leaf_begin, leaf_end;
+    // interleaved sharding (multi-GPU): CTAs are dealt to this launch in chunks of `chunk_blocks` consecutive
+    // CTAs, consecutive chunks of one launch lying `chunk_stride_blocks` CTAs apart in the leaf order
+    // (0: one contiguous range)
+    i64 chunk_blocks, chunk_stride_blocks;
     i64 n;
     int k;
     int row_order;
@@ -67,6 +71,7 @@ struct KnnParams {
     void* d2_out;
     u32* link_out;      // optional [n][link_cols] at the original point index; may live on a peer GPU
     int link_cols;
+    int link_by_position;   // 0: link_out row = original point index; 1: row = index position (warp-coalesced block stores)
     unsigned long long* stats;   // [KNN_NSTATS] or nullptr
     int warp_smem;
 };
@@ -364,7 +369,9 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // leaf and node indices fit 32 bits (n < 2^31, 32-point leaves): the traversal uses int arithmetic
-    const i64 ql64 = p.leaf_begin + (i64)blockIdx.x * WARPS + wib;
+    i64 gblock = blockIdx.x;
+    if (p.chunk_blocks > 0) gblock = (gblock / p.chunk_blocks) * p.chunk_stride_blocks + gblock % p.chunk_blocks;
+    const i64 ql64 = p.leaf_begin + gblock * WARPS + wib;
     if (ql64 >= p.leaf_end) return;
     const int ql = (int)ql64;
     const int K = p.k;
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         hk.st(m * 32 + lane, hk.ld(lane));
         heap_replace_root<T>(hk, m, lane, t);
     }
-    const i64 pos_row = (ql64 - p.leaf_begin) * LEAF + lane;
+    const i64 pos_row = ((i64)blockIdx.x * WARPS + wib) * LEAF + lane;      // row of this launch (row_order 1)
     if (s.active) {
         const i64 row = p.row_order == 0 ? (i64)my_id : pos_row;
         T* dd = (T*)p.d2_out + row * K;
@@ -675,7 +682,20 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>();
         }
     }
-    if (p.link_out != nullptr && s.active) {
+    if (p.link_out != nullptr && p.link_by_position) {
+        // Position-ordered rows: the 32 rows of this leaf are one contiguous block of 32 * link_cols ids, written with
+        // full 128-byte warp stores -- the shape NVLink wants when link_out is a peer-mapped buffer (4-byte stores
+        // scattered by original index are one packet each and made the remote ranks packet-rate bound).  Padding
+        // lanes hold 0xffffffff ids; the consumer's un-permute pass skips them.
+        __syncwarp();
+        u32* blk = p.link_out + (ql64 * LEAF) * p.link_cols;
+        const int total = LEAF * p.link_cols;
+#pragma unroll 1
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / p.link_cols, c = e - r * p.link_cols;
+            blk[e] = KS::id(hk.ld(c * 32 + r));
+        }
+    } else if (p.link_out != nullptr && s.active) {
         // the exchange step of the multi-GPU path, fused into the epilogue: the k_link nearest ids go
         // straight to the consumer's buffer (a peer-mapped pointer over NVLink on ranks other than the owner)
         u32* lo_ = p.link_out + (i64)my_id * p.link_cols;
@@ -701,6 +721,12 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
 template <typename T, int D>
 static int launch_knn(const KnnParams& p, cudaStream_t st) {
     i64 n_q = p.leaf_end - p.leaf_begin;
+    if (p.chunk_blocks > 0) {
+        // leaves of this launch: every chunk that starts before leaf_end, whole chunks (the kernel skips leaves past the end)
+        const i64 stride_leaves = p.chunk_stride_blocks * WARPS, chunk_leaves = p.chunk_blocks * WARPS;
+        const i64 n_chunks = n_q <= 0 ? 0 : (n_q + stride_leaves - 1) / stride_leaves;
+        n_q = n_chunks * chunk_leaves;
+    }
     if (n_q <= 0) return AL_OK;
     size_t smem = (size_t)p.warp_smem * WARPS;
     AL_REQUIRE(smem <= 227 * 1024, AL_EINVAL, "al_knn: k too large for shared memory");

@@ -140,10 +140,12 @@ extern "C" int al_rescale(const void* P, int dtype, int64_t n, int d, int64_t ro
 // rows are read with 128-bit loads when their pitch allows it (float: k % 4 == 0), which quarters the
 // number of L1 requests.  The per-row arithmetic is the reference's: T-precision sequential sum, ratio
 // in T, the rest in float64.
+struct DealMap { i64 begin, chunk, stride, end; };      // chunk == 0: rows are written in place
+
 template <typename T, bool VEC4>
 __global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, const u32* __restrict__ idx,
                                                      const double* __restrict__ weights, i64 nq, int k, double half_d,
-                                                     const u32* __restrict__ row_ids, T* __restrict__ out) {
+                                                     const u32* __restrict__ row_ids, DealMap dm, T* __restrict__ out) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     i64 orow = i;
@@ -151,6 +153,9 @@ __global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, c
         const u32 rid = row_ids[i];
         if (rid == 0xffffffffu) return;      // padding row of the last leaf
         orow = rid;
+    } else if (dm.chunk > 0) {
+        orow = dm.begin + (i / dm.chunk) * dm.stride + i % dm.chunk;      // index position of row i of a dealt launch
+        if (orow >= dm.end) return;
     }
     const T* r = d2 + i * k;
     const T coreT = r[k - 1];
@@ -186,8 +191,24 @@ extern "C" int al_logrho(const void* d2, const uint32_t* idx, const double* weig
     return al_logrho_rows(d2, idx, weights, dtype, nq, k, d_intrinsic, nullptr, logrho_out, stream);
 }
 
+static int logrho_launch(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k, int d_intrinsic,
+                         const uint32_t* row_ids, DealMap dm, void* logrho_out, void* stream);
+
 extern "C" int al_logrho_rows(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k,
                               int d_intrinsic, const uint32_t* row_ids, void* logrho_out, void* stream) {
+    return logrho_launch(d2, idx, weights, dtype, nq, k, d_intrinsic, row_ids, DealMap{0, 0, 0, 0}, logrho_out, stream);
+}
+
+extern "C" int al_logrho_dealt(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k,
+                               int d_intrinsic, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                               void* logrho_by_position_out, void* stream) {
+    AL_REQUIRE(chunk_positions > 0 && stride_positions >= chunk_positions, AL_EINVAL, "al_logrho_dealt: bad chunk/stride");
+    return logrho_launch(d2, idx, weights, dtype, nq, k, d_intrinsic, nullptr, DealMap{pos_begin, chunk_positions, stride_positions, pos_end},
+                         logrho_by_position_out, stream);
+}
+
+static int logrho_launch(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k, int d_intrinsic,
+                         const uint32_t* row_ids, DealMap dm, void* logrho_out, void* stream) {
     AL_REQUIRE(dtype == AL_F32 || dtype == AL_F64, AL_EINVAL, "al_logrho: bad dtype");
     AL_REQUIRE(nq >= 0 && k >= 1 && d_intrinsic >= 1, AL_EINVAL, "al_logrho: bad shape");
     AL_REQUIRE(weights == nullptr || idx != nullptr, AL_EINVAL, "al_logrho: weights need idx");
@@ -196,11 +217,11 @@ extern "C" int al_logrho_rows(const void* d2, const uint32_t* idx, const double*
     unsigned grid = (unsigned)((nq + 255) / 256);
     if (dtype == AL_F32) {
         if (k % 4 == 0 && ((uintptr_t)d2 & 15) == 0)
-            logrho_kernel<float, true><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (float*)logrho_out);
+            logrho_kernel<float, true><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, dm, (float*)logrho_out);
         else
-            logrho_kernel<float, false><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (float*)logrho_out);
+            logrho_kernel<float, false><<<grid, 256, 0, st>>>((const float*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, dm, (float*)logrho_out);
     } else {
-        logrho_kernel<double, false><<<grid, 256, 0, st>>>((const double*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, (double*)logrho_out);
+        logrho_kernel<double, false><<<grid, 256, 0, st>>>((const double*)d2, idx, weights, nq, k, d_intrinsic / 2.0, row_ids, dm, (double*)logrho_out);
     }
     AL_CHECK_LAUNCH();
     return AL_OK;

@@ -19,6 +19,30 @@ def shard_positions(positions, rank, world, leaf=32):
     return lo, hi, per_leaves * leaf
 
 
+DEAL_CHUNK_LEAVES = 1024     # leaves per dealt chunk (32 768 points): small enough to average out regional cost differences,
+                             # large enough that a chunk's candidate tiles stay hot in L2
+
+
+def deal_chunks(positions, rank, world, leaf=32, chunk_leaves=DEAL_CHUNK_LEAVES):
+    """Interleaved sharding for the peer-memory exchange: the spatial order is cut into chunks of
+    `chunk_leaves` leaves dealt round-robin, rank r owning chunks r, r + world, r + 2 world, ...
+    -> (begin, chunk, stride, rows): arguments of al_knn_dealt (index positions) and its number of output rows."""
+    n_leaves = positions // leaf
+    # small clouds: at least ~8 chunks per rank (chunks are whole CTAs of 4 leaves)
+    chunk_leaves = max(4, min(chunk_leaves, ((n_leaves + world * 8 - 1) // (world * 8) + 3) // 4 * 4))
+    chunk = chunk_leaves * leaf
+    stride = world * chunk
+    begin = rank * chunk
+    rows = 0 if begin >= positions else (positions - begin + stride - 1) // stride * chunk
+    return begin, chunk, stride, rows
+
+
+def dealt_positions(begin, chunk, stride, rows, device):
+    """Index position searched by row i of a dealt launch (may run past the last position in the final chunk)."""
+    i = torch.arange(rows, device=device, dtype=torch.int64)
+    return begin + (i // chunk) * stride + i % chunk
+
+
 def gathered_rows(positions, world, leaf, device):
     """Row indices of the concatenated [world * per] gather buffer that hold real
     index positions 0..positions-1, in position order."""
@@ -37,6 +61,15 @@ class PeerBuffers:
     def __init__(self, dist):
         self.dist = dist
         self.cache = {}
+        self.epoch = 0
+
+    def next_epoch(self):
+        """Collective (every rank, once per exchange).  Exchanges alternate between two sets of buffers: ranks that
+        have nothing to do after the exchange start their next run early and may already store its rows while rank 0
+        still reads the previous set; they cannot get further ahead than that because the next exchange's barrier
+        needs rank 0."""
+        self.epoch += 1
+        return self.epoch & 1
 
     def get(self, name, shape, dtype, device):
         """Collective: every rank calls with identical arguments.  Returns a _native.PeerArray backed by rank 0's

@@ -239,14 +239,22 @@ def run_b200(args):
     dP = P_pin_t.to(dev)
     torch.cuda.synchronize(dev)
 
+    debug = os.environ.get("AL_BENCH_DEBUG") is not None
+
     def one_run(resident):
+        t0 = time.perf_counter()
         c = AstroLink(P_pin, dist=D, **kwargs)
         if resident:
             c._use_device_input(dP)
+        t1 = time.perf_counter()
         c.run()
+        t2 = time.perf_counter()
         if rank == 0:
             # touch every result the user reads (D2H happens inside run(); these are host arrays already)
             _ = (c.logRho[0], c.ordering[0], c.groups.shape, c.prominences.shape, c.clusters.shape)
+        if debug and rank == 0:
+            t3 = time.perf_counter()
+            print(f"[bench] construct {1e3*(t1-t0):.2f} ms  run {1e3*(t2-t1):.2f} ms  touch {1e3*(t3-t2):.2f} ms", file=sys.stderr)
         return c
 
     def timed(resident, steps):
@@ -259,7 +267,10 @@ def run_b200(args):
         marks[0].record()
         last = None
         for i in range(steps):
+            tr = time.perf_counter()
             last = None                       # release the previous step's buffers first (as a caller re-running would)
+            if debug and rank == 0:
+                print(f"[bench] release {1e3*(time.perf_counter()-tr):.2f} ms", file=sys.stderr)
             last = one_run(resident)
             marks[i + 1].record()
         e1.record()
@@ -294,9 +305,11 @@ def run_b200(args):
         tmax = t.clone()
         td.all_reduce(t, op=td.ReduceOp.SUM)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
-        pairs_total, knn_ms = int(t[0].item()), float(tmax[1].item())
+        tmin = torch.tensor([stage["knn"]], dtype=torch.float64, device=dev)
+        td.all_reduce(tmin, op=td.ReduceOp.MIN)
+        pairs_total, knn_ms, knn_ms_min = int(t[0].item()), float(tmax[1].item()), float(tmin[0].item())
     else:
-        pairs_total, knn_ms = pairs, stage["knn"]
+        pairs_total, knn_ms, knn_ms_min = pairs, stage["knn"], stage["knn"]
     if rank != 0:
         if D is not None:
             import torch.distributed as td
@@ -351,6 +364,7 @@ def run_b200(args):
                                      "(68% issue-slot utilisation in profiles/r01_knn_c4_ncu_summary.txt): tree pruning and per-query "
                                      "selection, not distance arithmetic, dominate its instruction stream"},
         "stage_ms": stages_out,
+        "knn_ms_over_ranks": {"min": round(knn_ms_min, 3), "max": round(knn_ms, 3)},
         "host_timers_ms": host_timers,
         "hbm_passes": others,
     }

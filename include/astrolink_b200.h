@@ -92,6 +92,21 @@ int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row
 int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order, uint32_t* idx_out, void* d2_out,
                 uint32_t* link_out, int link_cols, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
 
+/* a3 for one rank of a query-sharded run: the leaves of the spatial order are dealt to the
+ * ranks in chunks so that every rank gets a sample of all regions (per-query cost varies with the local
+ * structure of the cloud).  This launch searches the index positions
+ *   [pos_begin + c * stride_positions, pos_begin + c * stride_positions + chunk_positions)  for c = 0, 1, ...
+ * below pos_end; rank r of R passes pos_begin = r * chunk_positions, stride_positions = R * chunk_positions.
+ * link_out rows are written in index-position order ([positions][link_cols], full 128-byte warp stores: the
+ * consumer un-permutes them with al_scatter_rows), not by original index as in al_knn_link.
+ * Rows are written in launch order (row_order must be 1): row i of the output is position
+ * pos_begin + (i / chunk_positions) * stride_positions + i % chunk_positions; rows past pos_end are not written.
+ * al_knn_dealt_rows gives the number of output rows.  chunk_positions == 0: identical to al_knn_link. */
+int64_t al_knn_dealt_rows(int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions);
+int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                 int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
+                 unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- a4/a5: _compute_logRho_njit / _compute_weighted_logRho_njit
  *      (astrolink.py:293-303, gather of weights[indices] at :283) ----------
  * out[i] = log((sum_j w_j - sum_j w_j d2[i][j] / d2[i][k-1]) / d2[i][k-1]^(d_intrinsic/2)),
@@ -99,6 +114,12 @@ int al_knn_link(const void* index, int64_t pos_begin, int64_t pos_end, int k, in
  * float64, stored in `dtype` (as the reference's store at :282). */
 int al_logrho(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq,
               int k, int d_intrinsic, void* logrho_out, void* stream);
+/* a4/a5 for the rows of an al_knn_dealt launch: row i is written at its index position
+ * pos_begin + (i / chunk_positions) * stride_positions + i % chunk_positions of logrho_by_position_out (rows past
+ * pos_end are skipped).  Consecutive threads store consecutive elements, so the output may be a peer-mapped buffer. */
+int al_logrho_dealt(const void* d2, const uint32_t* idx, const double* weights, int dtype, int64_t nq, int k, int d_intrinsic,
+                    int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                    void* logrho_by_position_out, void* stream);
 
 /* as al_logrho, but row i is written to logrho_out[row_ids[i]] (row_ids == 0xffffffff: skipped); logrho_out may be
  * a peer-mapped pointer (multi-GPU: every rank scatters its densities into the consumer's array). */

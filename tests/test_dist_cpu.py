@@ -73,3 +73,23 @@ def test_shard_positions_cover_everything():
             assert lo == min(covered, positions) or lo == covered
             covered = max(covered, hi)
         assert covered == positions
+
+
+def test_dealt_chunks_cover_every_position_once():
+    """deal_chunks/dealt_positions (the interleaved sharding of the peer-memory path): over all ranks the rows
+    inside the cloud are exactly the index positions 0..positions-1, each once."""
+    from astrolink_b200 import dist as adist
+    for positions in (32, 4000 // 32 * 32 + 32, 150016, 10_000_000 // 32 * 32 + 32):
+        for world in (1, 2, 3, 4, 8):
+            seen = torch.zeros(positions, dtype=torch.int32)
+            for r in range(world):
+                begin, chunk, stride, rows = adist.deal_chunks(positions, r, world)
+                assert chunk % (32 * 4) == 0 and stride == world * chunk and begin == r * chunk
+                if rows == 0:
+                    assert begin >= positions
+                    continue
+                assert rows % chunk == 0
+                pos = adist.dealt_positions(begin, chunk, stride, rows, "cpu")
+                assert int(pos[0]) == begin and int(pos.max()) < positions + chunk
+                seen.index_add_(0, pos[pos < positions], torch.ones(int((pos < positions).sum()), dtype=torch.int32))
+            assert bool((seen == 1).all()), (positions, world)
