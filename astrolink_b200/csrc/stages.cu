@@ -485,12 +485,13 @@ extern "C" int al_sort_edges(const void* weights, int dtype, const uint32_t* pai
 template <typename V>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const V* __restrict__ src, const u32* __restrict__ perm, i64 rows, int cols,
                                                            int src_stride, int dst_stride, V* __restrict__ dst) {
-    i64 total = rows * cols;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        i64 r = t / cols;
-        int c = (int)(t - r * cols);
-        u32 to = perm[r];
-        if (to != 0xffffffffu) dst[(i64)to * dst_stride + c] = src[r * src_stride + c];
+    // one thread per row: the permutation entry is read once and the (short) row is copied with a column loop
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
+        const u32 to = perm[r];
+        if (to == 0xffffffffu) continue;
+        const V* s = src + r * src_stride;
+        V* d = dst + (i64)to * dst_stride;
+        for (int c = 0; c < cols; c++) d[c] = s[c];
     }
 }
 
@@ -500,9 +501,9 @@ extern "C" int al_scatter_rows(const void* src, const uint32_t* perm, int64_t ro
     if (rows <= 0) return AL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (elem_bytes == 4)
-        scatter_rows_kernel<u32><<<al_grid(rows * cols, 256), 256, 0, st>>>((const u32*)src, perm, rows, cols, src_stride, dst_stride, (u32*)dst);
+        scatter_rows_kernel<u32><<<al_grid(rows, 256), 256, 0, st>>>((const u32*)src, perm, rows, cols, src_stride, dst_stride, (u32*)dst);
     else
-        scatter_rows_kernel<u64><<<al_grid(rows * cols, 256), 256, 0, st>>>((const u64*)src, perm, rows, cols, src_stride, dst_stride, (u64*)dst);
+        scatter_rows_kernel<u64><<<al_grid(rows, 256), 256, 0, st>>>((const u64*)src, perm, rows, cols, src_stride, dst_stride, (u64*)dst);
     AL_CHECK_LAUNCH();
     return AL_OK;
 }

@@ -154,3 +154,74 @@ def test_w1_objective_kernel_vs_numpy(G, dtype):
     f_ref, ok1 = stats.fit_prominence_model(prom[:, 1])
     f_gpu, ok2 = stats.fit_prominence_model(None, objective=obj, p_sorted=obj.sorted)
     assert ok1 and ok2 and np.allclose(f_ref, f_gpu, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,d,world,chunk_leaves", [(30011, 6, 3, 8), (20000, 3, 2, 64), (9000, 2, 4, 4), (30011, 6, 8, 1024)])
+def test_knn_dealt_launches_equal_one_launch(n, d, world, chunk_leaves):
+    """The sharded stage on one GPU: the `world` dealt launches (al_knn_dealt + al_logrho_dealt, rows sent in
+    index-position order, un-permuted with al_scatter_rows) reproduce the single launch bit for bit, and the
+    k_link columns written by the epilogue (al_knn_link) equal the first columns of the full rows."""
+    from astrolink_b200 import dist as adist
+    nat = _native()
+    rng = np.random.default_rng(n + d)
+    P = rng.normal(size=(n, d)).astype(np.float32)
+    P[: n // 3] *= 0.05                                  # a dense clump: regional differences in search cost
+    index = nat.Index(_cu(P))
+    K, L = 20, 7
+    link = torch.full((n, L), -7, dtype=torch.int32, device="cuda")
+    d2_ref, idx_ref = index.knn(K, link_out=link)
+    assert (link == idx_ref[:, :L]).all()
+    raw_ref = nat.logrho(d2_ref, idx_ref, K, d)
+    # link columns only (no full index rows)
+    link2 = torch.full((n, L), -7, dtype=torch.int32, device="cuda")
+    d2_b, idx_b = index.knn(K, link_out=link2, want_idx=False)
+    assert idx_b is None and (link2 == link).all() and (d2_b == d2_ref).all()
+
+    positions = index.positions
+    knn_pos = torch.full((positions, L), -5, dtype=torch.int32, device="cuda")
+    raw_pos = torch.full((positions,), float("nan"), dtype=torch.float32, device="cuda")
+    covered = 0
+    for r in range(world):
+        begin, chunk, stride, rows = adist.deal_chunks(positions, r, world, nat.LEAF, chunk_leaves)
+        d2, idx = index.knn(K, pos_begin=begin, pos_end=positions, row_order=1, link_out=knn_pos, want_idx=False,
+                            chunk=chunk, stride=stride)
+        assert d2.shape[0] == rows and idx is None
+        nat.logrho_dealt(d2, None, K, d, begin, positions, chunk, stride, raw_pos)
+        covered += rows
+    assert covered >= positions
+    perm = index.perm()
+    kNN = torch.full((n, L), -9, dtype=torch.int32, device="cuda")
+    raw = torch.full((n,), float("nan"), dtype=torch.float32, device="cuda")
+    nat.scatter_rows(knn_pos, perm, kNN)
+    nat.scatter_rows(raw_pos.view(-1, 1), perm, raw.view(-1, 1))
+    torch.cuda.synchronize()
+    assert (kNN == idx_ref[:, :L]).all(), "dealt launches must reproduce the single launch"
+    assert (raw == raw_ref).all()
+
+
+@pytest.mark.parametrize("L,stride,dtype", [(7, 7, np.float32), (7, 20, np.float32), (9, 9, np.float64), (2, 2, np.float32),
+                                            (18, 18, np.float32), (40, 40, np.float64)])
+def test_make_edges_layouts_vs_oracle(L, stride, dtype):
+    """a8 with contiguous and strided neighbour rows, short and long rows (staged kernel and its fallback), both dtypes."""
+    from oracle import oracle
+    nat = _native()
+    n = 5003
+    rng = np.random.default_rng(L * 100 + stride)
+    lr = rng.random(n).astype(dtype)
+    lr[rng.integers(0, n, 300)] = lr[7]                  # ties
+    knn = np.empty((n, L), dtype=np.uint32)
+    for i in range(n):
+        others = rng.choice(n - 1, L - 1, replace=False)
+        others[others >= i] += 1
+        row = np.concatenate(([i], others))
+        if i % 5 == 0:
+            rng.shuffle(row)                             # the point itself is not always in column 0
+        knn[i] = row
+    pairs_o, edges_o = oracle.make_graph(lr, knn)
+    full = np.zeros((n, stride), dtype=np.uint32)
+    full[:, :L] = knn
+    dk = torch.from_numpy(full.view(np.int32)).cuda()[:, :L]
+    w, pairs = nat.make_edges(_cu(lr), dk, L)
+    torch.cuda.synchronize()
+    assert (w.cpu().numpy() == edges_o).all()
+    assert (nat.u32_numpy(pairs) == pairs_o).all()
