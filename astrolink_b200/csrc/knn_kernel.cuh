@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     s.n_push = 0;
     s.n_insert = 0;
     u32 n_flush = 0, n_iter = 0, n_loaded = 0, n_eval = 0, n_needy = 0, n_slow = 0;
-    unsigned long long n_pairs = 0;
+    u32 n_qt = 0;       // (query, tile) evaluations: 32 pairs each
     // the query box: tight bounds of the own leaf (level-0 box arrays)
     T qlo[D], qhi[D];
     {
@@ -511,9 +511,10 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             int bit;
             if (KNN_ORDER && t_h == 1) {
                 // leaves: nearest box first, so the k-th distances tighten as early as possible
-                const u32 key = ((t_mask >> lane) & 1u) ? top_dist : 0xffffffffu;
-                const u32 mn = __reduce_min_sync(FULL, key);
-                bit = __ffs(__ballot_sync(FULL, key == mn)) - 1;
+                // the lane number rides in the low 5 bits of the key (the order is a heuristic: 27 bits of distance are plenty),
+                // so one warp reduction yields both the minimum and who holds it
+                const u32 key = ((t_mask >> lane) & 1u) ? ((top_dist & ~31u) | (u32)lane) : 0xffffffffu;
+                bit = (int)(__reduce_min_sync(FULL, key) & 31u);
             } else {
                 bit = __ffs(t_mask) - 1;
             }
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         }
     };
 
-    u32 phase = 0;
+    u32 seq = 0, pend_t = 0;    // tiles issued so far / number of the pending tile: tile t lands in buffer t & 1 on phase (t >> 1) & 1
     int pending = -1;
     u32 pending_need = 0;
     int bi = 0;                 // buffer the next issue goes to
@@ -564,12 +565,11 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 tma_load_1d(wbase + (u32)bi * (u32)p.tile_stride, p.tiles + (size_t)(u32)cand * (u32)p.tile_stride, (u32)p.tile_stride,
                             &bars[bi]);
             }
-            n_loaded++;
+            if (KNN_STATS) n_loaded++;
         }
         if (pending >= 0) {
             const int bw = bi ^ 1;
-            while (!mbar_try_wait(&bars[bw], (phase >> bw) & 1u)) {}
-            phase ^= (1u << bw);
+            while (!mbar_try_wait(&bars[bw], (pend_t >> 1) & 1u)) {}
             const unsigned char* tile = wbase + (u32)bw * (u32)p.tile_stride;
             const T* hdr = (const T*)tile;
             const T* tcoord = (const T*)(tile + p.tile_hdr_bytes);
@@ -595,8 +595,8 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
             const int n_need = __popc(need);
             if (KNN_BRUTE || n_need > SPARSE_MAX) {
                 // ---- dense: every lane evaluates all 32 candidates (packed f32x2)
-                n_eval++;
-                n_pairs += (unsigned long long)LEAF * 32;
+                if (KNN_STATS) n_eval++;
+                n_qt += 32;
                 const u32 coords = tile_sa + (u32)bw * (u32)p.tile_stride + (u32)p.tile_hdr_bytes;
                 // each chunk may push 2*CHUNK_PB entries per lane; the sparse path can leave queues fuller than that allows
                 if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
@@ -622,8 +622,8 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 }
             } else if (n_need > 0) {
                 // ---- sparse: two needy queries per pass, lane l evaluates candidate l for both
-                n_eval++;
-                n_pairs += (unsigned long long)LEAF * n_need;
+                if (KNN_STATS) n_eval++;
+                n_qt += n_need;
                 T cc[D];
 #pragma unroll
                 for (int j = 0; j < D; j++) cc[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
@@ -652,6 +652,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         if (!lookahead) { pending = -1; continue; }
         if (cand < 0) break;
         pending = cand;
+        pend_t = seq++;
         pending_need = cneed;
         bi ^= 1;
     }
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     if (p.stats != nullptr) {
         const u32 pushes = __reduce_add_sync(FULL, s.n_push), inserts = __reduce_add_sync(FULL, s.n_insert);
         if (lane == 0) {
-            atomicAdd(p.stats + 0, n_pairs);                                         // (query, candidate) pairs evaluated
+            atomicAdd(p.stats + 0, (unsigned long long)n_qt * LEAF);                                         // (query, candidate) pairs evaluated
             atomicAdd(p.stats + 1, (unsigned long long)n_loaded);                       // tiles fetched by TMA
             atomicAdd(p.stats + 2, (unsigned long long)n_eval);                         // tiles evaluated
             atomicAdd(p.stats + 3, (unsigned long long)n_needy);                        // lanes that needed a fetched tile

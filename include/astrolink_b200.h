@@ -78,8 +78,8 @@ const uint32_t* al_index_perm(const void* index);
  *              0xffffffff / +inf).
  * pairs_evaluated (device uint64[8], may be NULL) accumulates kernel statistics
  * for roofline accounting: [0] (query, candidate) distance evaluations,
- * [1] tiles fetched, [2] tiles evaluated, [3] lanes needing a tile, [4] queue
- * pushes, [5] top-k insertions, [6] merge iterations, [7] lanes needing a tile before the refresh. */
+ * and, in diagnostic builds (-DKNN_STATS=1) only, [1] tiles fetched, [2] tiles evaluated, [3] lanes needing a
+ * tile, [4] queue pushes, [5] top-k insertions, [6] merge iterations, [7] lanes needing a tile before the refresh. */
 size_t al_knn_workspace_bytes(int dtype, int64_t n, int d, int k);
 int al_knn(const void* index, int64_t pos_begin, int64_t pos_end, int k, int row_order,
            uint32_t* idx_out, void* d2_out, unsigned long long* pairs_evaluated,
