@@ -481,14 +481,13 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
 
     // ---- traversal state: ancestors of the own leaf, bottom-up; a small stack for descents.
     // The top entry (children mask, node, level) lives in registers; lower entries in shared memory.
-    int anc = 0;    // 0: own leaf not yet emitted; g >= 1: next ancestor level to open
+    int anc = 1;    // next ancestor level of the own leaf to open
     int sp = 0;     // entries on the stack, including the register-resident top
     u32 t_mask = 0;
     int t_node = 0;
     int t_h = 0;
     u32 cand_need = FULL;
     auto next_candidate = [&]() -> int {
-        if (anc == 0) { anc = 1; cand_need = FULL; return ql; }
         for (;;) {
             if (sp == 0) {
                 if (anc > p.n_levels) return -1;
@@ -549,112 +548,124 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         }
     };
 
-    u32 seq = 0, pend_t = 0;    // tiles issued so far / number of the pending tile: tile t lands in buffer t & 1 on phase (t >> 1) & 1
-    int pending = -1;
-    u32 pending_need = 0;
-    int bi = 0;                 // buffer the next issue goes to
-    for (;;) {
-        // no look-ahead while the own leaf is pending: box tests need the queries and their first bounds
-        const bool lookahead = pending != ql;
-        const int cand = lookahead ? next_candidate() : -1;
-        const u32 cneed = cand_need;
-        if (cand >= 0) {
-            __syncwarp();       // every lane is done reading buffer bi
-            if (lane == 0) {
-                mbar_expect_tx(&bars[bi], (u32)p.tile_stride);
-                tma_load_1d(wbase + (u32)bi * (u32)p.tile_stride, p.tiles + (size_t)(u32)cand * (u32)p.tile_stride, (u32)p.tile_stride,
-                            &bars[bi]);
-            }
-            if (KNN_STATS) n_loaded++;
+    // Tile t of this warp lands in buffer t & 1 and completes phase (t >> 1) & 1 of that buffer's barrier.
+    auto issue_tile = [&](int leaf, u32 buf) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[buf], (u32)p.tile_stride);
+            tma_load_1d(wbase + buf * (u32)p.tile_stride, p.tiles + (size_t)(u32)leaf * (u32)p.tile_stride, (u32)p.tile_stride,
+                        &bars[buf]);
         }
-        if (pending >= 0) {
-            const int bw = bi ^ 1;
-            while (!mbar_try_wait(&bars[bw], (pend_t >> 1) & 1u)) {}
-            const unsigned char* tile = wbase + (u32)bw * (u32)p.tile_stride;
-            const T* hdr = (const T*)tile;
-            const T* tcoord = (const T*)(tile + p.tile_hdr_bytes);
-            const u32* ids = (const u32*)(tile + p.tile_ids_off);
-            u32 need;
-            if (pending == ql) {
-                // own leaf: pick up this lane's query point and publish it in the query table
-#pragma unroll
-                for (int j = 0; j < D; j++) {
-                    s.q[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
-                    qtab[lane * RS + j] = s.q[j];
-                }
-                my_id = ids[lane];
-                s.active = my_id != 0xffffffffu;
-                s.worst = s.active ? inf_t<T>() : (T)-1;
-                qworst[0] = s.worst;
-                __syncwarp();
-                need = FULL;
-            } else {
-                need = pending_need;
-                if (KNN_STATS) { n_needy += __popc(need); n_slow += __popc(need); }
-            }
-            const int n_need = __popc(need);
-            if (KNN_BRUTE || n_need > SPARSE_MAX) {
-                // ---- dense: every lane evaluates all 32 candidates (packed f32x2)
-                if (KNN_STATS) n_eval++;
-                n_qt += 32;
-                const u32 coords = tile_sa + (u32)bw * (u32)p.tile_stride + (u32)p.tile_hdr_bytes;
-                // each chunk may push 2*CHUNK_PB entries per lane; the sparse path can leave queues fuller than that allows
-                if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
+        if (KNN_STATS) n_loaded++;
+    };
+    auto wait_tile = [&](u32 t) {
+        while (!mbar_try_wait(&bars[t & 1u], (t >> 1) & 1u)) {}
+    };
+
+    // distances from the queries in `need` to the 32 candidates of the tile in buffer `bw`
+    auto eval_tile = [&](u32 bw, u32 need) {
+        const unsigned char* tile = wbase + bw * (u32)p.tile_stride;
+        const T* tcoord = (const T*)(tile + p.tile_hdr_bytes);
+        const u32* ids = (const u32*)(tile + p.tile_ids_off);
+        const int n_need = __popc(need);
+        if (KNN_BRUTE || n_need > SPARSE_MAX) {
+            // ---- dense: every lane evaluates all 32 candidates (packed f32x2)
+            if (KNN_STATS) n_eval++;
+            n_qt += 32;
+            const u32 coords = tile_sa + bw * (u32)p.tile_stride + (u32)p.tile_hdr_bytes;
+            // each chunk may push 2*CHUNK_PB entries per lane; the sparse path can leave queues fuller than that allows
+            if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
 #pragma unroll 1
-                for (int pb0 = 0; pb0 < LEAF / 2; pb0 += CHUNK_PB) {
-                    T v[2 * CHUNK_PB];
-                    chunk_dist<D>(s.q, coords, p.pair_block, pb0, v);
-                    T mn = v[0];
+            for (int pb0 = 0; pb0 < LEAF / 2; pb0 += CHUNK_PB) {
+                T v[2 * CHUNK_PB];
+                chunk_dist<D>(s.q, coords, p.pair_block, pb0, v);
+                T mn = v[0];
 #pragma unroll
-                    for (int e = 1; e < 2 * CHUNK_PB; e++) mn = v[e] < mn ? v[e] : mn;
-                    if (__any_sync(FULL, mn <= s.worst)) {
+                for (int e = 1; e < 2 * CHUNK_PB; e++) mn = v[e] < mn ? v[e] : mn;
+                if (__any_sync(FULL, mn <= s.worst)) {
 #pragma unroll
-                        for (int e = 0; e < 2 * CHUNK_PB; e++) {
-                            if (v[e] <= s.worst) {
-                                qk.st(s.cnt * 32 + lane, KS::make(v[e], ids[2 * pb0 + e]));
-                                s.cnt++;
-                                if (KNN_STATS) s.n_push++;
-                            }
+                    for (int e = 0; e < 2 * CHUNK_PB; e++) {
+                        if (v[e] <= s.worst) {
+                            qk.st(s.cnt * 32 + lane, KS::make(v[e], ids[2 * pb0 + e]));
+                            s.cnt++;
+                            if (KNN_STATS) s.n_push++;
                         }
-                        if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB))
-                            flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
                     }
-                }
-            } else if (n_need > 0) {
-                // ---- sparse: two needy queries per pass, lane l evaluates candidate l for both
-                if (KNN_STATS) n_eval++;
-                n_qt += n_need;
-                T cc[D];
-#pragma unroll
-                for (int j = 0; j < D; j++) cc[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
-                const u32 cid = ids[lane];
-                u32 m = need;
-#pragma unroll 1
-                while (m) {
-                    // two needy queries per pass (two independent scalar chains, see pair_dist)
-                    const int qa = __ffs(m) - 1;
-                    m &= m - 1;
-                    const bool two = m != 0;
-                    const int qb = two ? __ffs(m) - 1 : qa;
-                    m &= m - 1;
-                    T ra[RS], rb[RS];
-                    load_row<RS>(qtab + qa * RS, ra);
-                    load_row<RS>(qtab + qb * RS, rb);
-                    T va, vb;
-                    pair_dist<D>(ra, rb, cc, va, vb);
-                    const u32 ha = __ballot_sync(FULL, va <= ra[D]);
-                    const u32 hb = two ? __ballot_sync(FULL, vb <= rb[D]) : 0u;
-                    if (ha) emit_hits(ha, va, cid, qa);
-                    if (hb) emit_hits(hb, vb, cid, qb);
+                    if (__any_sync(FULL, s.cnt > QCAP - 2 * CHUNK_PB))
+                        flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
                 }
             }
+        } else if (n_need > 0) {
+            // ---- sparse: two needy queries per pass, lane l evaluates candidate l for both
+            if (KNN_STATS) n_eval++;
+            n_qt += n_need;
+            T cc[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) cc[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
+            const u32 cid = ids[lane];
+            u32 m = need;
+#pragma unroll 1
+            while (m) {
+                // two needy queries per pass (two independent scalar chains, see pair_dist)
+                const int qa = __ffs(m) - 1;
+                m &= m - 1;
+                const bool two = m != 0;
+                const int qb = two ? __ffs(m) - 1 : qa;
+                m &= m - 1;
+                T ra[RS], rb[RS];
+                load_row<RS>(qtab + qa * RS, ra);
+                load_row<RS>(qtab + qb * RS, rb);
+                T va, vb;
+                pair_dist<D>(ra, rb, cc, va, vb);
+                const u32 ha = __ballot_sync(FULL, va <= ra[D]);
+                const u32 hb = two ? __ballot_sync(FULL, vb <= rb[D]) : 0u;
+                if (ha) emit_hits(ha, va, cid, qa);
+                if (hb) emit_hits(hb, vb, cid, qb);
+            }
         }
-        if (!lookahead) { pending = -1; continue; }
-        if (cand < 0) break;
-        pending = cand;
-        pend_t = seq++;
-        pending_need = cneed;
-        bi ^= 1;
+    };
+
+    // ---- own leaf (tile 0, no look-ahead: the box tests need the queries and their first bounds)
+    issue_tile(ql, 0u);
+    wait_tile(0u);
+    {
+        const unsigned char* tile = wbase;
+        const T* tcoord = (const T*)(tile + p.tile_hdr_bytes);
+        const u32* ids = (const u32*)(tile + p.tile_ids_off);
+        // pick up this lane's query point and publish it in the query table
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            s.q[j] = tcoord[(lane >> 1) * p.pair_block + 2 * j + (lane & 1)];
+            qtab[lane * RS + j] = s.q[j];
+        }
+        my_id = ids[lane];
+        s.active = my_id != 0xffffffffu;
+        s.worst = s.active ? inf_t<T>() : (T)-1;
+        qworst[0] = s.worst;
+        __syncwarp();
+        eval_tile(0u, FULL);
+    }
+    // ---- the other leaves: while tile t is evaluated, the traversal has already found tile t + 1 and its copy is in flight
+    anc = 1;
+    int cur = next_candidate();
+    if (cur >= 0) {
+        u32 cur_need = cand_need;
+        u32 t = 1;
+        issue_tile(cur, 1u);
+#pragma unroll 1
+        for (;;) {
+            const int nxt = next_candidate();
+            const u32 nxt_need = cand_need;
+            if (nxt >= 0) {
+                __syncwarp();       // every lane is done reading the other buffer
+                issue_tile(nxt, (t & 1u) ^ 1u);
+            }
+            wait_tile(t);
+            if (KNN_STATS) { n_needy += __popc(cur_need); n_slow += __popc(cur_need); }
+            eval_tile(t & 1u, cur_need);
+            if (nxt < 0) break;
+            cur_need = nxt_need;
+            t++;
+        }
     }
     if (__any_sync(FULL, s.cnt > 0)) flush_queues<T, D>(s, qk, hk, qworst, K, lane, n_flush, n_iter);
 
