@@ -361,7 +361,7 @@ def run_b200(args):
                      "brute_force_equiv_tflops": (float(n) * n * 3 * d) / (knn_ms * 1e-3) / 1e12 / world,
                      "peak_source": "FP32 FMA issue rate measured in this run (al_fp32_peak_tflops); MEASURED_PEAKS.json has no FP32 figure",
                      "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak; the kernel is instruction-issue bound "
-                                     "(68% issue-slot utilisation in profiles/r01_knn_c4_ncu_summary.txt): tree pruning and per-query "
+                                     "(69% issue-slot utilisation in profiles/r01_knn_c4_ncu_summary.txt): tree pruning and per-query "
                                      "selection, not distance arithmetic, dominate its instruction stream"},
         "stage_ms": stages_out,
         "knn_ms_over_ranks": {"min": round(knn_ms_min, 3), "max": round(knn_ms, 3)},
