@@ -36,6 +36,17 @@
 #ifndef KNN_QCAP
 #define KNN_QCAP 8
 #endif
+// Branch-trimming switches, each measured on C4 (tools/knn_tournament.py): 92.9 ms with all three off,
+// 92.0 / 91.6 / 90.1 ms with one on, 88.7 ms with all three.  0 selects the earlier code for A/B runs.
+#ifndef KNN_W4
+#define KNN_W4 1               // one predicate per flush step
+#endif
+#ifndef KNN_W5
+#define KNN_W5 1               // sift-down with a clamped right child (no branch on its existence)
+#endif
+#ifndef KNN_W8
+#define KNN_W8 1               // one combined vote per sparse pass, the per-query ballots only when something hit
+#endif
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 5
 #endif
@@ -245,10 +256,18 @@ __device__ __forceinline__ void heap_replace_root(const KeyStore<T>& h, int K, i
         if (l >= K) break;
         int c = l;
         typename KS::Key ck = h.ld(l * 32 + lane);
+#if KNN_W5
+        {
+            const int r = l + 1 < K ? l + 1 : l;        // a missing right child reads the left one again: never "worse"
+            const typename KS::Key rk = h.ld(r * 32 + lane);
+            if (KS::worse(rk, ck)) { c = r; ck = rk; }
+        }
+#else
         if (l + 1 < K) {
             const typename KS::Key rk = h.ld((l + 1) * 32 + lane);
             if (KS::worse(rk, ck)) { c = l + 1; ck = rk; }
         }
+#endif
         if (!KS::worse(ck, v)) break;
         h.st(pos * 32 + lane, ck);
         pos = c;
@@ -275,6 +294,14 @@ __device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<
     if (KNN_STATS) { n_flush++; n_iter += maxc; }
 #pragma unroll 1
     for (int t = 0; t < maxc; t++) {
+#if KNN_W4
+        const typename KS::Key v = qk.ld(t * 32 + lane);          // slots past cnt hold stale keys: masked by the test below
+        if (t < s.cnt && KS::worse(s.root, v)) {
+            heap_replace_root<T>(hk, K, lane, v);
+            s.root = hk.ld(lane);
+            if (KNN_STATS) s.n_insert++;
+        }
+#else
         if (t < s.cnt) {
             const typename KS::Key v = qk.ld(t * 32 + lane);
             if (KS::worse(s.root, v)) {
@@ -283,6 +310,7 @@ __device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<
                 if (KNN_STATS) s.n_insert++;
             }
         }
+#endif
     }
     s.cnt = 0;
     if (s.active) s.worst = KS::dist(s.root);
@@ -616,10 +644,22 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 load_row<RS>(qtab + qb * RS, rb);
                 T va, vb;
                 pair_dist<D>(ra, rb, cc, va, vb);
+#if KNN_W8
+                const bool hit_a = va <= ra[D], hit_b = two && vb <= rb[D];
+                if (__any_sync(FULL, hit_a || hit_b)) {      // the common pass has no hit at all: one vote, one branch
+                    const u32 ha = __ballot_sync(FULL, hit_a);
+                    const u32 hb = __ballot_sync(FULL, hit_b);
+                    if (ha) emit_hits(ha, va, cid, qa);
+                    if (hb) emit_hits(hb, vb, cid, qb);
+                }
+#else
                 const u32 ha = __ballot_sync(FULL, va <= ra[D]);
                 const u32 hb = two ? __ballot_sync(FULL, vb <= rb[D]) : 0u;
-                if (ha) emit_hits(ha, va, cid, qa);
-                if (hb) emit_hits(hb, vb, cid, qb);
+                if (ha | hb) {      // the common pass has no hit at all: one branch
+                    if (ha) emit_hits(ha, va, cid, qa);
+                    if (hb) emit_hits(hb, vb, cid, qb);
+                }
+#endif
             }
         }
     };
