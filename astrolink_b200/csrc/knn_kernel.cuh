@@ -3,15 +3,20 @@
 // (reference astrolink/astrolink.py:279).
 //
 // One warp owns one leaf of 32 queries (one query per lane).  It walks the
-// 32-ary box hierarchy of the index bottom-up from its own leaf (one lane tests
-// one child box), and for every surviving candidate leaf pulls that leaf's
-// 32-point tile into shared memory with a TMA bulk copy (cp.async.bulk +
-// mbarrier, double buffered: the next tile is in flight while the current one
-// is evaluated) and evaluates the 32 x 32 distances on the FP32 pipe with
-// packed f32x2 SUB/FMA (two candidates per instruction).  Candidates that beat
-// a lane's current k-th distance go to a per-lane queue in shared memory; when
-// a queue is close to full the whole warp merges its queues into per-lane
-// sorted top-k lists held in registers (k <= 32) or local memory (k <= 128).
+// 32-ary box hierarchy of the index bottom-up from its own leaf.  Opening a wide
+// node, lane j takes child j: a box-to-box bound against the warp's bound, then,
+// for every query that still needs the parent, the distance from that query to
+// the child's box against the query's own k-th distance -- a 32-bit need mask
+// per child.  Needed leaves are pulled into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier, double buffered: while tile t is evaluated the
+// traversal has already found tile t+1 and its copy is in flight).  A tile that
+// many queries need is evaluated densely (every lane all 32 candidates, packed
+// f32x2 SUB/FMA, two candidates per instruction); otherwise lane l holds
+// candidate l and the needy queries are evaluated two per pass.  Candidates
+// that beat a lane's current k-th distance go to a per-lane queue in shared
+// memory; when a queue is close to full the warp merges the queues into
+// per-lane max-heaps in shared memory ([slot][lane], conflict-free), heap-sorted
+// in place at the end.  k is a runtime value (<= 128).
 //
 // Exactness: the distance is acc = fma(q_j - p_j, q_j - p_j, acc), j ascending,
 // in the data dtype -- the same chain as the oracle -- and lists are ordered by
