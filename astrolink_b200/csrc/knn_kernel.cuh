@@ -43,14 +43,14 @@
 #endif
 // Branch-trimming switches, each measured on C4 (tools/knn_tournament.py): 92.9 ms with all three off,
 // 92.0 / 91.6 / 90.1 ms with one on, 88.7 ms with all three.  0 selects the earlier code for A/B runs.
-#ifndef KNN_W4
-#define KNN_W4 1               // one predicate per flush step
+#ifndef KNN_FLUSH_ONE_PREDICATE
+#define KNN_FLUSH_ONE_PREDICATE 1               // one predicate per flush step
 #endif
-#ifndef KNN_W5
-#define KNN_W5 1               // sift-down with a clamped right child (no branch on its existence)
+#ifndef KNN_SIFT_CLAMPED_CHILD
+#define KNN_SIFT_CLAMPED_CHILD 1               // sift-down with a clamped right child (no branch on its existence)
 #endif
-#ifndef KNN_W8
-#define KNN_W8 1               // one combined vote per sparse pass, the per-query ballots only when something hit
+#ifndef KNN_SPARSE_ONE_VOTE
+#define KNN_SPARSE_ONE_VOTE 1               // one combined vote per sparse pass, the per-query ballots only when something hit
 #endif
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 5
@@ -261,7 +261,7 @@ __device__ __forceinline__ void heap_replace_root(const KeyStore<T>& h, int K, i
         if (l >= K) break;
         int c = l;
         typename KS::Key ck = h.ld(l * 32 + lane);
-#if KNN_W5
+#if KNN_SIFT_CLAMPED_CHILD
         {
             const int r = l + 1 < K ? l + 1 : l;        // a missing right child reads the left one again: never "worse"
             const typename KS::Key rk = h.ld(r * 32 + lane);
@@ -299,7 +299,7 @@ __device__ __forceinline__ void flush_queues(WarpState<T, D>& s, const KeyStore<
     if (KNN_STATS) { n_flush++; n_iter += maxc; }
 #pragma unroll 1
     for (int t = 0; t < maxc; t++) {
-#if KNN_W4
+#if KNN_FLUSH_ONE_PREDICATE
         const typename KS::Key v = qk.ld(t * 32 + lane);          // slots past cnt hold stale keys: masked by the test below
         if (t < s.cnt && KS::worse(s.root, v)) {
             heap_replace_root<T>(hk, K, lane, v);
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
                 load_row<RS>(qtab + qb * RS, rb);
                 T va, vb;
                 pair_dist<D>(ra, rb, cc, va, vb);
-#if KNN_W8
+#if KNN_SPARSE_ONE_VOTE
                 const bool hit_a = va <= ra[D], hit_b = two && vb <= rb[D];
                 if (__any_sync(FULL, hit_a || hit_b)) {      // the common pass has no hit at all: one vote, one branch
                     const u32 ha = __ballot_sync(FULL, hit_a);
