@@ -50,6 +50,7 @@ _SIGS = {
     "al_knn_link": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
     "al_knn_dealt": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
     "al_knn_dealt_rows": (_i64, [_i64, _i64, _i64, _i64]),
+    "al_knn_density": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _int, _vp, _vp, _sz, _vp]),
     "al_logrho_dealt": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _i64, _i64, _i64, _i64, _vp, _vp]),
     "al_logrho_rows": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _vp, _vp, _vp]),
     "al_enable_peer_access": (_int, [_int]),
@@ -154,24 +155,29 @@ class Index:
         return self.buf[256:256 + 4 * self.positions].view(torch.int32)
 
     def knn(self, k, pos_begin=0, pos_end=None, row_order=0, count_pairs=False, link_out=None, want_idx=True,
-            chunk=0, stride=0):
+            chunk=0, stride=0, logrho_out=None, d_intrinsic=None, want_d2=True):
         """a3: exact kNN of the points at index positions [pos_begin, pos_end).  link_out: optional
         [n, L] int32 tensor (possibly peer-mapped) that receives the L nearest ids at the original row;
         with want_idx=False (link_out required) the full [rows, k] index array is not written (idx is None).
         chunk/stride (positions): search the dealt chunks [pos_begin + c*stride, +chunk) below pos_end
-        (al_knn_dealt; row_order must be 1, rows in launch order)."""
+        (al_knn_dealt; row_order must be 1, rows in launch order).
+        logrho_out (+ d_intrinsic): a4 fused into the search (al_knn_density) -- the unweighted raw log-density goes to
+        logrho_out[original index] (index position for dealt launches); with want_d2=False the distance rows are not
+        written at all (d2 is None)."""
         L = lib()
         pos_end = self.positions if pos_end is None else pos_end
         rows = self.n if row_order == 0 else int(L.al_knn_dealt_rows(pos_begin, pos_end, chunk, stride))
         assert want_idx or link_out is not None
+        assert want_d2 or logrho_out is not None
         idx = torch.empty((rows, k), dtype=torch.int32, device=self.device) if want_idx else None
-        d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device)
+        d2 = torch.empty((rows, k), dtype=self.dtype, device=self.device) if want_d2 else None
         pairs = torch.zeros(8, dtype=torch.int64, device=self.device) if count_pairs else None
-        ws = _ws(L.al_knn_workspace_bytes(_dt(d2), self.n, self.d, k), self.device)
+        ws = _ws(L.al_knn_workspace_bytes(AL_F32 if self.dtype == torch.float32 else AL_F64, self.n, self.d, k), self.device)
         link_cols = 0 if link_out is None else int(link_out.shape[1])
         if rows > 0:
-            _check(L.al_knn_dealt(_ptr(self.buf), pos_begin, pos_end, chunk, stride, k, row_order, _ptr(idx), _ptr(d2), _ptr(link_out),
-                                  link_cols, _ptr(pairs), _ptr(ws), ws.numel(), _stream()), "al_knn_dealt")
+            _check(L.al_knn_density(_ptr(self.buf), pos_begin, pos_end, chunk, stride, k, row_order, _ptr(idx), _ptr(d2), _ptr(link_out),
+                                    link_cols, _ptr(logrho_out), int(d_intrinsic or 0), _ptr(pairs), _ptr(ws), ws.numel(), _stream()),
+                   "al_knn_density")
         if count_pairs:
             return d2, idx, pairs
         return d2, idx

@@ -272,13 +272,20 @@ class AstroLink:
                 # the k_link nearest ids go straight to their own [n, k_link] array (astrolink.py:286) from the
                 # search kernel's epilogue; the full index rows are only written when the weights need them
                 kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
-                d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=w is not None)
-                b.record()
-                a, b = self._stage("density")
-                a.record()
-                raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
-                b.record()
-                del d2, idx
+                if w is None:
+                    # a4 fused into the search epilogue (al_knn_density): the [n, k_den] distance array is never written
+                    raw = torch.empty((n,), dtype=Pt.dtype, device=self._device)
+                    _, _, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=False,
+                                                      logrho_out=raw, d_intrinsic=self.d_intrinsic, want_d2=False)
+                    b.record()
+                else:
+                    d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=True)
+                    b.record()
+                    a, b = self._stage("density")
+                    a.record()
+                    raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
+                    b.record()
+                    del d2, idx
             else:
                 raw, kNN = self._sharded_knn(index, w, rank, world)
             # with the peer exchange only rank 0 holds the densities (results live on rank 0)
@@ -342,11 +349,18 @@ class AstroLink:
         begin, chunk, stride, rows = adist.deal_chunks(P_, rank, self._world()[1], nat.LEAF)
         a, b = self._stage("knn")
         a.record()
-        d2, idx, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True,
-                                             link_out=knn0, want_idx=w is not None, chunk=chunk, stride=stride)
-        b.record()
-        nat.logrho_dealt(d2, idx, K, self.d_intrinsic, begin, P_, chunk, stride, raw0, weights=w)
-        del d2, idx
+        if w is None:
+            # density fused into the search epilogue: both results go straight to rank 0 (position order)
+            _, _, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True, link_out=knn0,
+                                              want_idx=False, chunk=chunk, stride=stride, logrho_out=raw0,
+                                              d_intrinsic=self.d_intrinsic, want_d2=False)
+            b.record()
+        else:
+            d2, idx, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True,
+                                                 link_out=knn0, want_idx=True, chunk=chunk, stride=stride)
+            b.record()
+            nat.logrho_dealt(d2, idx, K, self.d_intrinsic, begin, P_, chunk, stride, raw0, weights=w)
+            del d2, idx
         a, b = self._stage("all_gather")
         a.record()
         torch.cuda.synchronize(self._device)      # this rank's peer stores are complete ...

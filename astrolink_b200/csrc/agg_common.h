@@ -51,6 +51,9 @@ AGG_HD inline u32 agg_atomic_min(u32* p, u32 v) {
 #endif
 }
 
+// plain load the compiler may not hoist or fuse (values other threads are updating: pointer jumping)
+AGG_HD inline u32 agg_load_relaxed(const u32* p) { return *(const volatile u32*)p; }
+
 AGG_HD inline int agg_log2_ceil(u64 x) {
     int b = 0;
     while (((u64)1 << b) < x) b++;

@@ -121,7 +121,13 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     uint2_agg* epB = ar.get<uint2_agg>(E);
     u32* erA = ar.get<u32>(E);
     u32* erB = ar.get<u32>(E);
+    // device-side totals of the prefix sums: the host reads them in batches (one read per Boruvka round, three in
+    // phase B) instead of once per scan
+    u32* tot = ar.get<u32>(16);
     if (!ar.ok) return -2;
+    x.fill_u32(tot, 0, 16);
+    u32* err = tot + 8;                  // consistency checks evaluated on the device, read with the last batch
+    const i64 nodefirst_cap = 2 * n + MAX_LEVELS * 64 + 64;
 
     i64 lvl_off[MAX_LEVELS + 1], lvl_nodes[MAX_LEVELS + 1], lvl_node_off[MAX_LEVELS + 1];
 
@@ -143,8 +149,9 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         u32* newid = ar.get<u32>(N + 1);
         u32* pickflag = ar.get<u32>(m + 1);
         u32* pkpos = ar.get<u32>(m + 1);
-        u32* changed = ar.get<u32>(1);
+        u32* changed = ar.get<u32>(8);
         if (!ar.ok) return -2;
+        if (node_off + N > nodefirst_cap) return -2;
         u32* nodefirst = nodefirst_all + node_off;
         x.fill_u32(first, NONE, N);
         x.fill_u32(pickflag, 0, m + 1);
@@ -167,32 +174,39 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 pickflag[i] = 1;
             });
         }
-        // pointer jumping to the component roots
-        for (int it = 0; it < 64; it++) {
-            x.fill_u32(changed, 0, 1);
-            // every vertex chases its pointer a bounded number of hops and stores where it got to; concurrent
-            // stores only ever replace a pointer by an ancestor, so stale reads are safe
+        // Pointer jumping to the component roots.  Every vertex chases its pointer up to 24 hops and stores where it got
+        // to; concurrent stores only ever replace a pointer by an ancestor, so stale reads are safe.  One pass divides
+        // every depth by at least 24, so 7 passes reach the roots from any depth below 24^7 > 2^32: a fixed number of
+        // launches, and no host round trip to find out when to stop -- a pass returns at once when the one before it
+        // found every vertex at its root.
+        x.fill_u32(changed, 0, 8);
+        for (int it = 0; it < 7; it++) {
+            const u32* prev = it > 0 ? changed + (it - 1) : nullptr;
+            u32* cur = changed + it;
             x.template launch<TagJump>(N, AGG_LAMBDA(i64 s) {
-                u32 h = hook[s];
+                if (prev != nullptr && agg_load_relaxed(prev) == 0u) return;
+                u32 h = agg_load_relaxed(hook + s);
                 const u32 h0 = h;
                 bool at_root = false;
                 for (int hop = 0; hop < 24; hop++) {
-                    const u32 hh = hook[h];
+                    const u32 hh = agg_load_relaxed(hook + h);
                     if (hh == h) { at_root = true; break; }
                     h = hh;
                 }
                 if (h != h0) hook[s] = h;
-                if (!at_root) *changed = 1;
+                if (!at_root) *cur = 1u;
             });
-            if (x.read_u32(changed) == 0) break;
         }
-        x.template launch<TagRoots>(N, AGG_LAMBDA(i64 s) { flag[s] = hook[s] == (u32)s ? 1u : 0u; });
-        const i64 Nn = x.exclusive_sum_u32(flag, newid, N, ar);
+        x.template launch<TagRoots>(N, AGG_LAMBDA(i64 s) {
+            flag[s] = hook[s] == (u32)s ? 1u : 0u;
+            if (s == 0 && changed[6] != 0u) err[0] = 1u;        // the jumping did not converge (cannot happen below 24^7 vertices)
+        });
+        x.exclusive_sum_u32(flag, newid, N, ar, tot + 0);
         // label[s] kept in flag[]
         x.template launch<TagLabel>(N, AGG_LAMBDA(i64 s) { flag[s] = newid[hook[s]]; });
         const u32* label = flag;
-        const i64 cnt = x.exclusive_sum_u32(pickflag, pkpos, m, ar);
-        if (M + cnt > n) return -4;
+        x.exclusive_sum_u32(pickflag, pkpos, m, ar, tot + 1);
+        // every picked edge merges two components, so M + cnt = n - Nn <= n: the records below stay inside pk_*[n]
         {
             const uint2_agg* e_ = ep;
             const u32* r_ = er;
@@ -219,7 +233,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 u32 i = first[s];
                 nodefirst[s] = i == NONE ? NONE : (u32)(M_ + pkpos[i]);
             });
-            const i64 m_next = x.exclusive_sum_u32(keep, pkpos, m, ar);
+            x.exclusive_sum_u32(keep, pkpos, m, ar, tot + 2);
             uint2_agg* eo = ep_next;
             u32* ro = er_next;
             x.template launch<TagCompact>(m, AGG_LAMBDA(i64 i) {
@@ -232,6 +246,11 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 eo[o] = ne;
                 ro[o] = r_ ? r_[i] : (u32)i;
             });
+            // the round's only host read: components, picked edges and surviving edges
+            u32 h3[3];
+            x.read_u32s(tot, h3, 3);
+            const i64 Nn = h3[0], cnt = h3[1], m_next = h3[2];
+            if (M + cnt > n || Nn + cnt != N) return -4;
             lvl_off[L] = M;
             lvl_nodes[L] = N;
             lvl_node_off[L] = node_off;
@@ -362,8 +381,8 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     uint2_agg* lb = ar.get<uint2_agg>(TL);   // pong
     if (!ar.ok) return -2;
     x.template launch<TagMisc>(M, AGG_LAMBDA(i64 c) { rflag[c] = par[c] == NONE ? 1u : 0u; });
-    const i64 nroots = x.exclusive_sum_u32(rflag, rpos, M, ar);
-    if (nroots != n_comp) return -7;
+    x.exclusive_sum_u32(rflag, rpos, M, ar, tot + 3);      // number of roots: checked against n_comp with the next read
+    const i64 nroots = n_comp;
     x.template launch<TagMisc>(M, AGG_LAMBDA(i64 c) { if (rflag[c]) roots[rpos[c]] = (u32)c; });
     x.template launch<TagTourSucc>(M, AGG_LAMBDA(i64 c) {
         const u32 k0 = child0[c], k1 = child1[c];
@@ -401,7 +420,11 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
             h ^= h >> 15;
             rflag2[e] = ((h & 31u) == 0u || (u32)e == headp[0]) ? 1u : 0u;
         });
-        const i64 nR = x.exclusive_sum_u32(rflag2, rid, TL, ar);
+        x.exclusive_sum_u32(rflag2, rid, TL, ar, tot + 4);
+        u32 h2[2];
+        x.read_u32s(tot + 3, h2, 2);
+        if ((i64)h2[0] != n_comp) return -7;
+        const i64 nR = h2[1];
         u32* relem = ar.get<u32>(nR + 1);
         uint2_agg* ra = ar.get<uint2_agg>(nR + 1);     // (next ruler id, elements up to the next ruler) ping
         uint2_agg* rb = ar.get<uint2_agg>(nR + 1);     // pong
@@ -494,7 +517,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
             });
             x.sort_pairs_u64_u32(ck_in, ck_out, cv_in, comp_order, n_comp, 64, ar);
             x.template launch<TagMisc>(n_comp, AGG_LAMBDA(i64 j) { csz[j] = size_int[roots[comp_order[j]]]; });
-            x.exclusive_sum_u32(csz, cex, n_comp, ar);
+            x.exclusive_sum_u32(csz, cex, n_comp, ar, tot + 7);
             x.template launch<TagMisc>(n_comp, AGG_LAMBDA(i64 j) { comp_off[comp_order[j]] = cex[j]; });
         }
         x.template launch<TagWeights>(M, AGG_LAMBDA(i64 c) {
@@ -543,7 +566,10 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         const u32 s0 = node_size(child0[c]), s1 = node_size(child1[c]);
         rowflag[c] = (s0 < s1 ? s0 : s1) >= 2 ? 1u : 0u;
     });
-    const i64 R0 = x.exclusive_sum_u32(rowflag, rowpos, M, ar);
+    x.exclusive_sum_u32(rowflag, rowpos, M, ar, tot + 5);
+    u32 hR0 = 0;
+    x.read_u32s(tot + 5, &hR0, 1);
+    const i64 R0 = hR0;
     const i64 R = R0 + (n_comp - 1);
     u32* r_geq = ar.get<u32>(R + 1);
     u32* r_leq = ar.get<u32>(R + 1);
@@ -646,7 +672,11 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     i64 G = 0;
     if (R > 0) {
         x.template launch<TagMisc>(R, AGG_LAMBDA(i64 r) { oflag[r] = r_size[r] > 2 ? 1u : 0u; });
-        G = x.exclusive_sum_u32(oflag, opos, R, ar);
+        x.exclusive_sum_u32(oflag, opos, R, ar, tot + 6);
+        u32 hG[3];
+        x.read_u32s(tot + 6, hG, 3);       // [6] groups, [7] (scratch of the component offsets), [8] device-side checks
+        if (hG[2] != 0u) return -8;
+        G = hG[0];
         if (G > 0) {
             x.template launch<TagMisc>(R, AGG_LAMBDA(i64 r) {
                 if (!oflag[r]) return;

@@ -89,3 +89,14 @@ __host__ __device__ static inline u64 f64_to_ordered(double f) {
 #endif
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
+
+#ifdef __CUDACC__
+// a4 raw log-density (astrolink.py:293-297): ln((k - S/c) / c^(d_int/2)) with S the T-precision sequential sum of
+// the k squared distances and c the largest one.  One definition shared by logrho_kernel and the kNN epilogues so
+// the fused and the stand-alone pass give the same bits.
+template <typename T>
+__device__ __forceinline__ T al_raw_logrho(T sum, T coreT, int k, double half_d) {
+    const double v = ((double)k - (double)(T)(sum / coreT)) / pow((double)coreT, half_d);
+    return (T)log(v);
+}
+#endif

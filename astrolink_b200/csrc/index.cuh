@@ -10,7 +10,8 @@
 //   [IndexHeader, 256 B]
 //   [perm: u32[NP]]                     index position -> original point (0xffffffff = padding)
 //   [tiles: NLf x tile_stride bytes]    per leaf: lo[d] hi[d] (T) | 16 pair blocks of PB T | ids u32[32]
-//   [boxes level 0..G: lo[d][count_h] then hi[d][count_h] (T, SoA)]
+//   [boxes level 0..G: count_h rows of box_stride T: lo_0 hi_0 lo_1 hi_1 ... (one row = one node, 16-byte aligned,
+//    so the lane that tests child c reads its whole box with 128-bit loads and (lo_j, hi_j) is one packed f32x2 operand)]
 #pragma once
 #include "common.cuh"
 
@@ -34,6 +35,7 @@ struct IndexHeader {
     int tile_hdr_bytes;    // lo/hi block, multiple of 16
     int tile_ids_off;      // byte offset of ids within a tile
     int pair_block;        // PB: elements of T per pair block (>= 2d)
+    int box_stride;        // BS: elements of T per box row (>= 2d, a multiple of 16 bytes)
 };
 
 constexpr u32 INDEX_MAGIC = 0xA5710B20u;
@@ -54,6 +56,7 @@ static inline void index_layout(int dtype, i64 n, int d, IndexHeader* h) {
     h->n_leaves = (n + LEAF - 1) / LEAF;
     int eb = elem_bytes(dtype);
     h->pair_block = pair_block_elems(dtype, d);
+    h->box_stride = pair_block_elems(dtype, d);
     h->tile_hdr_bytes = (int)al_align((size_t)2 * d * eb, 16);
     h->tile_ids_off = h->tile_hdr_bytes + (LEAF / 2) * h->pair_block * eb;
     h->tile_stride = (int)al_align((size_t)h->tile_ids_off + LEAF * 4, 128);
@@ -71,7 +74,7 @@ static inline void index_layout(int dtype, i64 n, int d, IndexHeader* h) {
     off += al_align((size_t)h->n_leaves * h->tile_stride);
     for (int l = 0; l <= g; l++) {
         h->box_off[l] = off;
-        off += al_align((size_t)2 * d * h->count[l] * eb);
+        off += al_align((size_t)h->box_stride * h->count[l] * eb);
     }
     h->total_bytes = off;
 }

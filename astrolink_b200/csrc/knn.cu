@@ -1,5 +1,6 @@
 // Host entry point of the kNN search (see knn_kernel.cuh for the kernel).
 #include "knn_kernel.cuh"
+#include <stdlib.h>
 
 #define DECL(T, D) int knn_launch_##T##_d##D(const KnnParams& p, cudaStream_t st);
 #define DECL_ALL(T) DECL(T, 1) DECL(T, 2) DECL(T, 3) DECL(T, 4) DECL(T, 5) DECL(T, 6) DECL(T, 7) DECL(T, 8) \
@@ -42,16 +43,27 @@ extern "C" int64_t al_knn_dealt_rows(int64_t pos_begin, int64_t pos_end, int64_t
 extern "C" int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
                             int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
                             unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream) {
+    AL_REQUIRE(d2_out != nullptr, AL_EINVAL, "al_knn: d2_out is NULL");
+    return al_knn_density(index, pos_begin, pos_end, chunk_positions, stride_positions, k, row_order, idx_out, d2_out, link_out, link_cols,
+                          nullptr, 0, pairs_evaluated, ws, ws_bytes, stream);
+}
+
+extern "C" int al_knn_density(const void* index, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                              int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
+                              void* logrho_out, int d_intrinsic, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes,
+                              void* stream) {
     (void)ws; (void)ws_bytes;
     AL_REQUIRE(chunk_positions >= 0 && (chunk_positions == 0 || (chunk_positions % (LEAF * WARPS) == 0 && stride_positions >= chunk_positions &&
                stride_positions % chunk_positions == 0)), AL_EINVAL,
                "al_knn_dealt: chunk_positions must be a multiple of %d and stride_positions a multiple of chunk_positions", LEAF * WARPS);
     AL_REQUIRE(chunk_positions == 0 || row_order == 1, AL_EINVAL, "al_knn_dealt: dealt chunks need row_order 1");
-    // link rows: dealt launches (the sharded path) write them in index-position order, everything else by original index
+    // link rows and fused densities: dealt launches (the sharded path) write them in index-position order, everything
+    // else by original index
     const int link_by_position = chunk_positions > 0 ? 1 : 0;
     AL_REQUIRE(link_out == nullptr || (link_cols >= 1 && link_cols <= k), AL_EINVAL, "al_knn_link: link_cols must be in [1, k]");
-    AL_REQUIRE(d2_out != nullptr, AL_EINVAL, "al_knn: d2_out is NULL");
+    AL_REQUIRE(d2_out != nullptr || logrho_out != nullptr, AL_EINVAL, "al_knn_density: d2_out may only be NULL when logrho_out is given");
     AL_REQUIRE(idx_out != nullptr || link_out != nullptr, AL_EINVAL, "al_knn: idx_out may only be NULL when link_out is given");
+    AL_REQUIRE(logrho_out == nullptr || d_intrinsic >= 1, AL_EINVAL, "al_knn_density: d_intrinsic must be >= 1");
     IndexHeader h;
     if (!index_lookup(index, &h)) {
         AL_CUDA(cudaMemcpy(&h, index, sizeof(h), cudaMemcpyDeviceToHost));
@@ -74,6 +86,7 @@ extern "C" int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_en
     p.tile_hdr_bytes = h.tile_hdr_bytes;
     p.tile_ids_off = h.tile_ids_off;
     p.pair_block = h.pair_block;
+    p.box_stride = h.box_stride;
     p.leaf_begin = pos_begin / LEAF;
     p.leaf_end = pos_end / LEAF;
     p.chunk_blocks = chunk_positions / (LEAF * WARPS);
@@ -86,10 +99,15 @@ extern "C" int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_en
     p.link_out = link_out;
     p.link_cols = link_cols;
     p.link_by_position = link_by_position;
+    p.logrho_out = logrho_out;
+    p.half_d = d_intrinsic / 2.0;
     p.stats = pairs_evaluated;
+    // AL_KNN_GENERIC=1 (development): float32 indices are searched by the generic kernel instead of the float32 one
+    static const bool generic = getenv("AL_KNN_GENERIC") != nullptr;
+    p.use_generic = generic ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (h.dtype == AL_F32) {
-        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride, k, h.d, h.n_levels);
+        p.warp_smem = knn_warp_smem_bytes<float>(h.tile_stride, k, h.d, h.n_levels);     // generic kernel; the float32 one sizes its own
         return g_knn_f32[h.d - 1](p, st);
     }
     p.warp_smem = knn_warp_smem_bytes<double>(h.tile_stride, k, h.d, h.n_levels);

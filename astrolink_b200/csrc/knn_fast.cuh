@@ -1,0 +1,609 @@
+// float32 specialisation of the exact kNN search kernel (the generic one is in
+// knn_kernel.cuh and still serves float64): replaces pykdtree's
+// KDTree.query(P_transform, k=k_den, sqr_dists=True) (reference
+// astrolink/astrolink.py:279), with the density of astrolink.py:293-297 fused
+// into its epilogue.
+//
+// Same algorithm, same arithmetic, same results as the generic kernel -- one warp
+// per 32-query leaf, 32-ary box hierarchy with per-child need masks, TMA tile
+// copies double-buffered per warp, per-lane queues merged into per-lane max-heaps
+// in shared memory -- rebuilt around the instruction counts of the round-1 ncu
+// capture (profiles/r02_knn_instruction_budget.md):
+//   * every shared-memory access goes through a 32-bit shared address computed once
+//     (no generic-address arithmetic, no re-derived window base in the loops);
+//     tile geometry is a compile-time function of D;
+//   * sparse tiles: a half-warp holds the whole tile, two candidates per lane as
+//     packed f32x2 operands straight from the pair-interleaved tile, so one pass
+//     evaluates two needy queries (one per half-warp) with D FADD2 + D FFMA2;
+//   * box tests: the index stores a node's box as interleaved (lo_j, hi_j) pairs, one
+//     128-bit-aligned row per node: a lane reads its child's box with 128-bit loads
+//     and a per-axis gap is one FADD2 (q - lo, q - hi), one 3-input max, one FFMA;
+//   * leaves of a wide node are visited nearest box first with one warp reduction
+//     per tile over a per-lane key register (no mask bookkeeping);
+//   * heap siblings are adjacent in shared memory, so a sift-down level is one
+//     128-bit load, two 64-bit compares and one store;
+//   * the query leaf's own box lives in shared memory instead of 2 D registers.
+#pragma once
+#include "knn_kernel.cuh"
+
+#ifndef KF_MINBLOCKS
+#define KF_MINBLOCKS 5
+#endif
+#ifndef KF_SPARSE_MAX
+#define KF_SPARSE_MAX 12       // tiles needed by at most this many queries take the sparse path
+#endif
+#ifndef KF_QCAP
+#define KF_QCAP 8
+#endif
+
+namespace kf {
+
+constexpr int QC = KF_QCAP;
+static_assert(QC >= 8, "the queue must absorb two dense chunks of four candidates");
+
+template <int D>
+struct Geo {
+    static constexpr int PB = (2 * D + 3) / 4 * 4;                  // floats per pair block (two candidates, interleaved)
+    static constexpr int PB4 = PB / 4;                              // 128-bit words per pair block
+    static constexpr int HDR = (2 * D * 4 + 15) / 16 * 16;          // bytes of the lo/hi header of a tile
+    static constexpr int IDS = HDR + (LEAF / 2) * PB * 4;           // byte offset of the ids inside a tile
+    static constexpr int TS = (IDS + LEAF * 4 + 127) / 128 * 128;   // tile stride (bytes)
+    static constexpr int RS = (D + 1 + 3) / 4 * 4;                  // floats per query-table row (coordinates, k-th distance)
+    static constexpr int RS4 = RS / 4;
+    static constexpr int BS = PB;                                   // floats per box row of the index
+};
+
+// per-warp shared memory (bytes from the warp's base):
+//   tiles[2] | queue [QC][32] u64 | heap root [32] u64 | heap pairs [K/2][32][2] u64 | query table [33][RS] f32 (row 32: a
+//   dummy query nothing is near to) | own leaf box [D] (lo, hi) | need masks [n_levels + 1][32] u32 | stack 3 x [8] | 2 mbarriers
+template <int D>
+static inline int warp_smem_bytes(int k, int n_levels) {
+    typedef Geo<D> G;
+    size_t b = 2 * (size_t)G::TS;
+    b += (size_t)QC * 256;
+    b += 256 + (size_t)(k / 2) * 512;
+    b += (size_t)33 * G::RS * 4;
+    b += (size_t)G::BS * 4;
+    b += (size_t)(n_levels + 1) * 128;
+    b += 3 * MAX_WIDE_LEVELS * 4;
+    b += 16;
+    return (int)al_align(b, 16);      // 16 bytes: what the bulk copies and the 128-bit loads need (d=6, k=20: 11 328 B, 5 CTAs/SM)
+}
+
+#ifdef __CUDACC__
+// ---- shared memory through 32-bit shared addresses -------------------------------------------------------------------
+__device__ __forceinline__ u32 lds32(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float ldsf(u32 a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ u64 lds64(u32 a) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds64x2(u32 a, u64& x, u64& y) { asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a)); }
+__device__ __forceinline__ void lds32x2(u32 a, u32& x, u32& y) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
+__device__ __forceinline__ void ldsf2(u32 a, float& x, float& y) { asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a)); }
+__device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void stsf(u32 a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts64x2(u32 a, u64 x, u64 y) { asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(a), "l"(x), "l"(y) : "memory"); }
+
+__device__ __forceinline__ void mbar_init_sa(u32 bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_sa(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_sa(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_sa(u32 bar, u32 parity) {
+    u32 ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ u64 make_key(float d, u32 id) { return ((u64)__float_as_uint(d) << 32) | id; }
+__device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((u32)(k >> 32)); }
+__device__ __forceinline__ u32 key_id(u64 k) { return (u32)k; }
+
+// row `q` of the query table (uniform or per-half-warp address: a broadcast load)
+template <int D>
+__device__ __forceinline__ void load_qrow(u32 row_sa, float* r) {
+#pragma unroll
+    for (int v = 0; v < Geo<D>::RS4; v++) {
+        const float4 f = lds_f4(row_sa + 16u * v);
+        r[4 * v] = f.x; r[4 * v + 1] = f.y; r[4 * v + 2] = f.z; r[4 * v + 3] = f.w;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(const KnnParams p) {
+    typedef Geo<D> G;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    i64 gblock = blockIdx.x;
+    if (p.chunk_blocks > 0) gblock = (gblock / p.chunk_blocks) * p.chunk_stride_blocks + gblock % p.chunk_blocks;
+    const i64 ql64 = p.leaf_begin + gblock * WARPS + wib;
+    if (ql64 >= p.leaf_end) return;
+    const int ql = (int)ql64;
+    const int K = p.k;
+    const int NP = K >> 1;                       // sibling pairs of the heap (node h's children live in pair h)
+    const int n_levels = p.n_levels;
+
+    // ---- shared addresses
+    const u32 tile_sa = smem_u32(smem) + (u32)wib * (u32)p.warp_smem;      // tile buffer 0
+    const u32 queue_sa = tile_sa + 2u * G::TS + (u32)lane * 8u;            // this lane's queue slot 0 (slot stride 256)
+    const u32 root_sa = tile_sa + 2u * G::TS + QC * 256u + (u32)lane * 8u; // this lane's heap root
+    const u32 pair_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)lane * 16u;     // this lane's pair 0 (pair stride 512)
+    const u32 qt_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)NP * 512u;        // query table
+    const u32 qbox_sa = qt_sa + 33u * G::RS * 4u;                          // own leaf's box, (lo_j, hi_j) pairs
+    const u32 need_sa = qbox_sa + G::BS * 4u;                              // [n_levels + 1][32] need masks
+    const u32 stk_sa = need_sa + (u32)(n_levels + 1) * 128u;               // stack: mask[8] | node[8] | level[8]
+    const u32 bar_sa = stk_sa + 3u * MAX_WIDE_LEVELS * 4u;                 // 2 mbarriers
+    const u32 myrow_sa = qt_sa + (u32)lane * (G::RS * 4u);
+
+    const u64 kinf = make_key(INFINITY, 0xffffffffu);
+    if (lane == 0) {
+        mbar_init_sa(bar_sa, 1);
+        mbar_init_sa(bar_sa + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the dummy query of an odd sparse pass: nothing is within distance -1 of it
+#pragma unroll
+        for (int j = 0; j < G::RS; j++) stsf(qt_sa + 32u * G::RS * 4u + 4u * j, j == D ? -1.f : 0.f);
+    }
+    sts64(root_sa, kinf);
+#pragma unroll 1
+    for (int h = 0; h < NP; h++) sts64x2(pair_sa + (u32)h * 512u, kinf, (2 * h + 2 < K) ? kinf : 0ull);   // a missing right sibling is never "worse"
+#pragma unroll
+    for (int j = 0; j < G::RS; j++) stsf(myrow_sa + 4u * j, j == D ? -1.f : 0.f);
+    if (lane < G::BS) stsf(qbox_sa + 4u * lane, ((const float*)p.box[0])[(size_t)ql * G::BS + lane]);
+    __syncwarp();
+
+    float q[D];
+    float worst = -1.f;         // k-th distance so far (-1: padding lane)
+    float bound = INFINITY;     // warp max of worst
+    u64 root = kinf;            // cached heap root
+    int cnt = 0;                // queue fill
+    u32 my_id = 0xffffffffu;
+    u32 n_qt = 0;               // (query, tile) evaluations
+    u32 st_loaded = 0, st_dense = 0, st_push = 0, st_insert = 0, st_rounds = 0, st_open_iter = 0, st_descents = 0;
+
+    // replace the heap root by v (v is better than the root) and restore the heap
+    auto sift = [&](u64 v) {
+        u32 hole = root_sa;
+        u32 pa = pair_sa;                   // pair h (the children of node h) of this lane
+        const u32 pa_end = pair_sa + (u32)NP * 512u;
+#pragma unroll 1
+        while (pa < pa_end) {
+            u64 c0, c1;
+            lds64x2(pa, c0, c1);
+            const u32 r8 = c1 > c0 ? 8u : 0u;
+            const u64 ck = r8 ? c1 : c0;
+            if (!(ck > v)) break;
+            sts64(hole, ck);
+            hole = pa + r8;
+            // node h's worse child is node 2h + 1 + r; in bytes from pair 0: off -> 2 off + 512 (1 + r)
+            pa = pair_sa + 2u * (pa - pair_sa) + 512u + (r8 << 6);
+        }
+        sts64(hole, v);
+    };
+
+    auto flush = [&]() {
+        const int maxc = __reduce_max_sync(FULL, cnt);
+#pragma unroll 1
+        for (int t = 0; t < maxc; t++) {
+            const u64 v = lds64(queue_sa + (u32)t * 256u);      // slots past cnt hold stale keys: masked by the test below
+            if (t < cnt && root > v) {
+                sift(v);
+                root = lds64(root_sa);
+                if (KNN_STATS) st_insert++;
+            }
+            if (KNN_STATS) st_rounds++;
+        }
+        cnt = 0;
+        if (my_id != 0xffffffffu) worst = key_dist(root);
+        stsf(myrow_sa + 4u * D, worst);
+        __syncwarp();
+        bound = warp_max_t<float>(worst);
+    };
+
+    // Open a wide node: lane j takes child j (a level-`hc` node), box-to-box test against the warp bound, then for every
+    // query in `qmask` the distance from the query to the child's box against the query's own k-th distance.  The child's
+    // need mask goes to shared memory at out_sa; `okey` becomes this lane's visiting-order key (box distance | lane).
+    u32 okey = 0xffffffffu;
+    auto open_node = [&](int hc, int node, int excl, u32 qmask, u32 out_sa) -> u32 {
+        const int count = (int)p.count[hc];
+        const int c = node * FANOUT + lane;
+        const bool ok = c < count && c != excl;
+        const float4* brow = reinterpret_cast<const float4*>((const float*)p.box[hc] + (size_t)(ok ? c : 0) * G::BS);
+        u64 bx[D + 1];
+#pragma unroll
+        for (int v = 0; v < G::PB4; v++) {
+            const float4 f = __ldg(brow + v);
+            if (2 * v < D) bx[2 * v] = pack2(f.x, f.y);
+            if (2 * v + 1 < D) bx[2 * v + 1] = pack2(f.z, f.w);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            float lo, hi, qlo, qhi;
+            unpack2(bx[j], lo, hi);
+            ldsf2(qbox_sa + 8u * j, qlo, qhi);
+            const float g = fmaxf(fmaxf(lo - qhi, qlo - hi), 0.f);
+            acc = __fmaf_rn(g, g, acc);
+        }
+        const bool pass = ok && acc <= bound;
+        u32 mask = 0;
+        if (__any_sync(FULL, pass)) {
+            u32 m = qmask;
+#pragma unroll 1
+            while (m) {
+                const u32 lb = m & (0u - m);        // lowest needy query, as a bit
+                m ^= lb;
+                const int qi = 31 - __clz(lb);
+                float row[G::RS];
+                load_qrow<D>(qt_sa + (u32)qi * (G::RS * 4u), row);
+                float pd = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    float a, b;
+                    unpack2(sub2(pack2(row[j], row[j]), bx[j]), a, b);      // (q - lo, q - hi)
+                    const float g = fmaxf(fmaxf(-a, b), 0.f);
+                    pd = __fmaf_rn(g, g, pd);
+                }
+                if (pd <= row[D]) mask |= lb;
+                if (KNN_STATS) st_open_iter++;
+            }
+            mask = pass ? mask : 0u;
+        }
+        sts32(out_sa + 4u * lane, mask);
+        okey = mask != 0 ? ((__float_as_uint(acc) & ~31u) | (u32)lane) : 0xffffffffu;      // order only: 27 bits of distance are plenty
+        return __ballot_sync(FULL, mask != 0);
+    };
+
+    // ---- traversal state: ancestors of the own leaf bottom-up; a small stack for descents (top entry in registers)
+    int anc = 1, sp = 0;
+    u32 t_mask = 0;
+    int t_node = 0, t_h = 0;
+    u32 cand_need = FULL;
+    auto next_candidate = [&]() -> int {
+        for (;;) {
+            if (sp == 0) {
+                if (anc > n_levels) return -1;
+                if (__any_sync(FULL, cnt > 0)) flush();
+                const int node = ql >> (5 * anc), excl = ql >> (5 * (anc - 1));
+                t_mask = open_node(anc - 1, node, excl, FULL, need_sa);
+                t_node = node;
+                t_h = anc;
+                __syncwarp();
+                sp = 1;
+                anc++;
+                continue;
+            }
+            if (t_h == 1) {
+                // leaves: nearest box first (the k-th distances tighten as early as possible); the lane number rides in
+                // the low bits of the key, so one reduction yields the minimum and who holds it
+                const u32 kmin = __reduce_min_sync(FULL, okey);
+                if (kmin != 0xffffffffu) {
+                    const u32 bit = kmin & 31u;
+                    if ((u32)lane == bit) okey = 0xffffffffu;
+                    cand_need = lds32(need_sa + ((u32)(sp - 1) * 32u + bit) * 4u);
+                    return t_node * FANOUT + (int)bit;
+                }
+                t_mask = 0;
+            }
+            if (t_mask == 0) {
+                sp--;
+                if (sp > 0) {
+                    t_mask = lds32(stk_sa + (u32)(sp - 1) * 4u);
+                    t_node = (int)lds32(stk_sa + (u32)(MAX_WIDE_LEVELS + sp - 1) * 4u);
+                    t_h = (int)lds32(stk_sa + (u32)(2 * MAX_WIDE_LEVELS + sp - 1) * 4u);
+                }
+                continue;
+            }
+            const int bit = __ffs(t_mask) - 1;
+            t_mask &= t_mask - 1;
+            const u32 need = lds32(need_sa + ((u32)(sp - 1) * 32u + (u32)bit) * 4u);
+            const int c = t_node * FANOUT + bit;
+            // descend: save the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
+            if (lane == 0) {
+                sts32(stk_sa + (u32)(sp - 1) * 4u, t_mask);
+                sts32(stk_sa + (u32)(MAX_WIDE_LEVELS + sp - 1) * 4u, (u32)t_node);
+                sts32(stk_sa + (u32)(2 * MAX_WIDE_LEVELS + sp - 1) * 4u, (u32)t_h);
+            }
+            if (KNN_STATS) st_descents++;
+            t_mask = open_node(t_h - 2, c, -1, need, need_sa + (u32)sp * 128u);
+            t_node = c;
+            t_h = t_h - 1;
+            __syncwarp();
+            sp++;
+        }
+    };
+
+    // Tile t of this warp lands in buffer t & 1 and completes phase (t >> 1) & 1 of that buffer's barrier.
+    auto issue_tile = [&](int leaf, u32 buf) {
+        if (lane == 0) {
+            mbar_expect_tx_sa(bar_sa + 8u * buf, (u32)G::TS);
+            tma_load_1d_sa(tile_sa + buf * (u32)G::TS, p.tiles + (size_t)(u32)leaf * (u32)G::TS, (u32)G::TS, bar_sa + 8u * buf);
+        }
+        if (KNN_STATS) st_loaded++;
+    };
+    auto wait_tile = [&](u32 t) {
+        while (!mbar_try_wait_sa(bar_sa + 8u * (t & 1u), (t >> 1) & 1u)) {}
+    };
+
+    // one hit of a sparse pass: owner lane `qi` queues the candidate held by lane `src`
+    auto emit = [&](u32 hm, float val, u32 id, int qi, int laneoff) {
+#pragma unroll 1
+        while (hm) {
+            const int b = __ffs(hm) - 1 + laneoff;
+            hm &= hm - 1;
+            const float vv = __shfl_sync(FULL, val, b);
+            const u32 ii = __shfl_sync(FULL, id, b);
+            if (__shfl_sync(FULL, cnt, qi) >= QC) flush();
+            if (lane == qi) {
+                sts64(queue_sa + (u32)cnt * 256u, make_key(vv, ii));
+                cnt++;
+                if (KNN_STATS) st_push++;
+            }
+        }
+    };
+
+    // distances from the queries in `need` to the 32 candidates of the tile in buffer `bw`
+    auto eval_tile = [&](u32 bw, u32 need) {
+        const u32 coords_sa = tile_sa + bw * (u32)G::TS + (u32)G::HDR;
+        const u32 ids_sa = tile_sa + bw * (u32)G::TS + (u32)G::IDS;
+        const int n_need = __popc(need);
+        if (KNN_BRUTE || n_need > KF_SPARSE_MAX) {
+            // ---- dense: every lane evaluates all 32 candidates, two per instruction (packed f32x2, broadcast tile reads)
+            if (KNN_STATS) st_dense++;
+            n_qt += 32;
+            if (__any_sync(FULL, cnt > QC - 4)) flush();        // the sparse path can leave queues fuller than a chunk allows
+#pragma unroll 1
+            for (int pb0 = 0; pb0 < LEAF / 2; pb0 += 2) {
+                float v[4];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    u64 acc = 0ull;
+#pragma unroll
+                    for (int v4 = 0; v4 < G::PB4; v4++) {
+                        const float4 f = lds_f4(coords_sa + (u32)((pb0 + c) * G::PB4 + v4) * 16u);
+                        if (2 * v4 < D) {
+                            const u64 df = sub2(pack2(q[2 * v4], q[2 * v4]), pack2(f.x, f.y));
+                            acc = fma2(df, df, acc);
+                        }
+                        if (2 * v4 + 1 < D) {
+                            const u64 df = sub2(pack2(q[2 * v4 + 1], q[2 * v4 + 1]), pack2(f.z, f.w));
+                            acc = fma2(df, df, acc);
+                        }
+                    }
+                    unpack2(acc, v[2 * c], v[2 * c + 1]);
+                }
+                const float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
+                if (__any_sync(FULL, mn <= worst)) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (v[e] <= worst) {
+                            sts64(queue_sa + (u32)cnt * 256u, make_key(v[e], lds32(ids_sa + (u32)(2 * pb0 + e) * 4u)));
+                            cnt++;
+                            if (KNN_STATS) st_push++;
+                        }
+                    }
+                    if (__any_sync(FULL, cnt > QC - 4)) flush();
+                }
+            }
+        } else if (n_need > 0) {
+            // ---- sparse: each half-warp holds the whole tile (lane l and l + 16: candidates 2 (l & 15) and 2 (l & 15) + 1 as
+            // packed pairs, exactly the tile's pair block), the lower half evaluates one needy query, the upper half another
+            n_qt += n_need;
+            const u32 hl = (u32)lane & 15u;
+            u64 cand[D + 1];
+#pragma unroll
+            for (int v4 = 0; v4 < G::PB4; v4++) {
+                const float4 f = lds_f4(coords_sa + hl * (G::PB * 4u) + 16u * v4);
+                if (2 * v4 < D) cand[2 * v4] = pack2(f.x, f.y);
+                if (2 * v4 + 1 < D) cand[2 * v4 + 1] = pack2(f.z, f.w);
+            }
+            u32 id0, id1;
+            lds32x2(ids_sa + hl * 8u, id0, id1);
+            u32 m = need;
+#pragma unroll 1
+            while (m) {
+                const int qa = __ffs(m) - 1;
+                m &= m - 1;
+                const int qb = m ? __ffs(m) - 1 : 32;       // odd count: the upper half takes the dummy query
+                m &= m - 1;
+                const int myq = lane < 16 ? qa : qb;
+                float row[G::RS];
+                load_qrow<D>(qt_sa + (u32)myq * (G::RS * 4u), row);
+                u64 acc = 0ull;
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    const u64 df = sub2(pack2(row[j], row[j]), cand[j]);
+                    acc = fma2(df, df, acc);
+                }
+                float d0, d1;
+                unpack2(acc, d0, d1);
+                const bool h0 = d0 <= row[D], h1 = d1 <= row[D];
+                if (__any_sync(FULL, h0 || h1)) {       // the common pass has no hit at all: one vote, one branch
+                    const u32 b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
+                    emit(b0 & 0xffffu, d0, id0, qa, 0);
+                    emit(b1 & 0xffffu, d1, id1, qa, 0);
+                    emit(b0 >> 16, d0, id0, qb, 16);
+                    emit(b1 >> 16, d1, id1, qb, 16);
+                }
+            }
+        }
+    };
+
+    // ---- own leaf (tile 0, no look-ahead: the box tests need the queries and their first bounds)
+    issue_tile(ql, 0u);
+    wait_tile(0u);
+    {
+        const u32 mine = tile_sa + (u32)G::HDR + (u32)(lane >> 1) * (G::PB * 4u) + (u32)(lane & 1) * 4u;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            q[j] = ldsf(mine + 8u * j);
+            stsf(myrow_sa + 4u * j, q[j]);
+        }
+        my_id = lds32(tile_sa + (u32)G::IDS + 4u * lane);
+        worst = my_id != 0xffffffffu ? INFINITY : -1.f;
+        stsf(myrow_sa + 4u * D, worst);
+        __syncwarp();
+        eval_tile(0u, FULL);
+    }
+    // ---- the other leaves: while tile t is evaluated, the traversal has already found tile t + 1 and its copy is in flight
+    int cur = next_candidate();
+    if (cur >= 0) {
+        u32 cur_need = cand_need;
+        u32 t = 1;
+        issue_tile(cur, 1u);
+#pragma unroll 1
+        for (;;) {
+            const int nxt = next_candidate();
+            const u32 nxt_need = cand_need;
+            if (nxt >= 0) {
+                __syncwarp();       // every lane is done reading the other buffer
+                issue_tile(nxt, (t & 1u) ^ 1u);
+            }
+            wait_tile(t);
+            eval_tile(t & 1u, cur_need);
+            if (nxt < 0) break;
+            cur_need = nxt_need;
+            t++;
+        }
+    }
+    if (__any_sync(FULL, cnt > 0)) flush();
+
+    // ---- heap -> ascending order in place (heapsort over the paired layout), then the outputs
+    auto node_sa = [&](int m, int r) -> u32 {       // heap node m of lane r
+        return m == 0 ? root_sa + (u32)(r - lane) * 8u : pair_sa + (u32)(r - lane) * 16u + (u32)((m - 1) >> 1) * 512u + (u32)((m - 1) & 1) * 8u;
+    };
+#pragma unroll 1
+    for (int m = K - 1; m >= 1; m--) {
+        const u64 v = lds64(node_sa(m, lane));
+        sts64(node_sa(m, lane), lds64(root_sa));
+        // sift v down from the root of a heap of m nodes
+        u32 hole = root_sa;
+        int h = 0;
+#pragma unroll 1
+        while (2 * h + 1 < m) {
+            u64 c0, c1;
+            lds64x2(pair_sa + (u32)h * 512u, c0, c1);
+            const bool r = (2 * h + 2 < m) && c1 > c0;
+            const u64 ck = r ? c1 : c0;
+            if (!(ck > v)) break;
+            sts64(hole, ck);
+            hole = pair_sa + (u32)h * 512u + (r ? 8u : 0u);
+            h = 2 * h + 1 + (r ? 1 : 0);
+        }
+        sts64(hole, v);
+    }
+    const bool active = my_id != 0xffffffffu;
+    const i64 pos_row = ((i64)blockIdx.x * WARPS + wib) * LEAF + lane;      // row of this launch (row_order 1)
+    if (active) {
+        const i64 row = p.row_order == 0 ? (i64)my_id : pos_row;
+        if (p.d2_out != nullptr) {
+            float* dd = (float*)p.d2_out + row * K;
+#pragma unroll 1
+            for (int m = 0; m < K; m++) dd[m] = key_dist(lds64(node_sa(m, lane)));
+        }
+        if (p.idx_out != nullptr) {
+            u32* io = p.idx_out + row * K;
+#pragma unroll 1
+            for (int m = 0; m < K; m++) io[m] = key_id(lds64(node_sa(m, lane)));
+        }
+        if (p.logrho_out != nullptr) {
+            // a4 (astrolink.py:293-297) fused: same arithmetic and summation order as logrho_kernel (stages.cu)
+            float sum = 0.f;
+#pragma unroll 1
+            for (int m = 0; m < K; m++) sum += key_dist(lds64(node_sa(m, lane)));
+            const i64 orow = p.link_by_position ? ql64 * LEAF + lane : (i64)my_id;
+            ((float*)p.logrho_out)[orow] = al_raw_logrho<float>(sum, key_dist(lds64(node_sa(K - 1, lane))), K, p.half_d);
+        }
+    } else if (p.row_order == 1) {
+#pragma unroll 1
+        for (int m = 0; m < K; m++) {
+            if (p.idx_out != nullptr) p.idx_out[pos_row * K + m] = 0xffffffffu;
+            if (p.d2_out != nullptr) ((float*)p.d2_out)[pos_row * K + m] = INFINITY;
+        }
+    }
+    if (p.link_out != nullptr && p.link_by_position) {
+        // Position-ordered rows: the 32 rows of this leaf are one contiguous block of 32 * link_cols ids, written with
+        // full 128-byte warp stores -- the shape NVLink wants when link_out is a peer-mapped buffer.  Padding lanes
+        // hold 0xffffffff ids; the consumer's un-permute pass skips them.
+        __syncwarp();
+        u32* blk = p.link_out + (ql64 * LEAF) * p.link_cols;
+        const int total = LEAF * p.link_cols;
+#pragma unroll 1
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / p.link_cols, c = e - r * p.link_cols;
+            blk[e] = key_id(lds64(node_sa(c, r)));
+        }
+    } else if (p.link_out != nullptr && active) {
+        u32* lo_ = p.link_out + (i64)my_id * p.link_cols;
+#pragma unroll 1
+        for (int m = 0; m < p.link_cols; m++) lo_[m] = key_id(lds64(node_sa(m, lane)));
+    }
+    if (p.stats != nullptr) {
+        // [0] (query, candidate) pairs evaluated; the rest are diagnostics (only maintained in KNN_STATS builds)
+        if (lane == 0) {
+            atomicAdd(p.stats + 0, (unsigned long long)n_qt * LEAF);
+            if (KNN_STATS) {
+                atomicAdd(p.stats + 1, (unsigned long long)st_loaded);          // tiles fetched
+                atomicAdd(p.stats + 2, (unsigned long long)st_dense);           // of which evaluated densely
+                atomicAdd(p.stats + 3, (unsigned long long)st_descents);        // wide nodes opened below the ancestors
+                atomicAdd(p.stats + 6, (unsigned long long)st_rounds);          // flush rounds
+                atomicAdd(p.stats + 7, (unsigned long long)st_open_iter);       // per-query iterations of the box tests
+            }
+        }
+        if (KNN_STATS) {
+            const u32 pushes = __reduce_add_sync(FULL, st_push), inserts = __reduce_add_sync(FULL, st_insert);
+            if (lane == 0) {
+                atomicAdd(p.stats + 4, (unsigned long long)pushes);
+                atomicAdd(p.stats + 5, (unsigned long long)inserts);
+            }
+        }
+    }
+}
+
+template <int D>
+static int launch(const KnnParams& p0, cudaStream_t st) {
+    typedef Geo<D> G;
+    KnnParams p = p0;
+    AL_REQUIRE(p.tile_stride == G::TS && p.tile_hdr_bytes == G::HDR && p.tile_ids_off == G::IDS && p.pair_block == G::PB &&
+               p.box_stride == G::BS, AL_EINTERNAL, "al_knn: index geometry does not match the float kernel's (d=%d)", D);
+    i64 n_q = p.leaf_end - p.leaf_begin;
+    if (p.chunk_blocks > 0) {
+        const i64 stride_leaves = p.chunk_stride_blocks * WARPS, chunk_leaves = p.chunk_blocks * WARPS;
+        const i64 n_chunks = n_q <= 0 ? 0 : (n_q + stride_leaves - 1) / stride_leaves;
+        n_q = n_chunks * chunk_leaves;
+    }
+    if (n_q <= 0) return AL_OK;
+    p.warp_smem = warp_smem_bytes<D>(p.k, p.n_levels);
+    const size_t smem = (size_t)p.warp_smem * WARPS;
+    AL_REQUIRE(smem <= 227 * 1024, AL_EINVAL, "al_knn: k too large for shared memory");
+    if (smem > 48 * 1024) AL_CUDA(cudaFuncSetAttribute(knn_fast_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_fast_kernel<D><<<(unsigned)((n_q + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(p);
+    AL_CHECK_LAUNCH();
+    return AL_OK;
+}
+#endif  // __CUDACC__
+
+}  // namespace kf

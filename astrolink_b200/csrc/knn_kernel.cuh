@@ -74,7 +74,7 @@ struct KnnParams {
     const void* box[MAX_WIDE_LEVELS];
     i64 count[MAX_WIDE_LEVELS];
     int n_levels;
-    int tile_stride, tile_hdr_bytes, tile_ids_off, pair_block;
+    int tile_stride, tile_hdr_bytes, tile_ids_off, pair_block, box_stride;
     i64 leaf_begin, leaf_end;
     // interleaved sharding (multi-GPU): CTAs are dealt to this launch in chunks of `chunk_blocks` consecutive
     // CTAs, consecutive chunks of one launch lying `chunk_stride_blocks` CTAs apart in the leaf order
@@ -88,8 +88,11 @@ struct KnnParams {
     u32* link_out;      // optional [n][link_cols] at the original point index; may live on a peer GPU
     int link_cols;
     int link_by_position;   // 0: link_out row = original point index; 1: row = index position (warp-coalesced block stores)
+    void* logrho_out;   // optional: raw log-density of every query (unweighted), fused into the epilogue; row as link_out's
+    double half_d;      // d_intrinsic / 2 (exponent of the core distance in the density)
     unsigned long long* stats;   // [KNN_NSTATS] or nullptr
     int warp_smem;
+    int use_generic;    // float32 only: 1 = search with this file's kernel instead of knn_fast.cuh's
 };
 
 // per-warp shared memory: 2 tiles | queue | heap | traversal stack | 2 mbarriers
@@ -453,13 +456,11 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     // the query box: tight bounds of the own leaf (level-0 box arrays)
     T qlo[D], qhi[D];
     {
-        const int cnt0 = (int)p.count[0];
-        const T* lo0 = (const T*)p.box[0];
-        const T* hi0 = lo0 + (i64)D * cnt0;
+        const T* b0 = (const T*)p.box[0] + (size_t)ql * p.box_stride;
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            qlo[j] = lo0[j * cnt0 + ql];
-            qhi[j] = hi0[j * cnt0 + ql];
+            qlo[j] = b0[2 * j];
+            qhi[j] = b0[2 * j + 1];
             s.q[j] = (T)0;
         }
     }
@@ -473,14 +474,13 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
         const int cnt = (int)p.count[hc];
         const int c = node * FANOUT + lane;
         const bool ok = c < cnt && c != excl;
-        const T* lo = (const T*)p.box[hc];
-        const T* hi_ = lo + (i64)D * cnt;
+        const T* brow = (const T*)p.box[hc] + (size_t)(ok ? c : 0) * p.box_stride;
         T blo[D], bhi[D];
         T acc = (T)0;
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            blo[j] = ok ? lo[j * cnt + c] : (T)0;        // D * cnt < 2^31
-            bhi[j] = ok ? hi_[j * cnt + c] : (T)0;
+            blo[j] = ok ? brow[2 * j] : (T)0;
+            bhi[j] = ok ? brow[2 * j + 1] : (T)0;
             T a = blo[j] - qhi[j], b = qlo[j] - bhi[j];
             const T g = gap_t(a, b);
             acc = fma_t<T>(g, g, acc);
@@ -724,19 +724,30 @@ __global__ void __launch_bounds__(WARPS * 32, KNN_MINBLOCKS) knn_kernel(const Kn
     const i64 pos_row = ((i64)blockIdx.x * WARPS + wib) * LEAF + lane;      // row of this launch (row_order 1)
     if (s.active) {
         const i64 row = p.row_order == 0 ? (i64)my_id : pos_row;
-        T* dd = (T*)p.d2_out + row * K;
+        if (p.d2_out != nullptr) {       // optional: the fused density below needs no distance rows in memory
+            T* dd = (T*)p.d2_out + row * K;
 #pragma unroll 1
-        for (int m = 0; m < K; m++) dd[m] = KS::dist(hk.ld(m * 32 + lane));
+            for (int m = 0; m < K; m++) dd[m] = KS::dist(hk.ld(m * 32 + lane));
+        }
         if (p.idx_out != nullptr) {      // optional: callers that only need the link columns pass NULL
             u32* io = p.idx_out + row * K;
 #pragma unroll 1
             for (int m = 0; m < K; m++) io[m] = KS::id(hk.ld(m * 32 + lane));
         }
+        if (p.logrho_out != nullptr) {
+            // a4 (astrolink.py:293-297) fused: the sorted distances are still in shared memory.  Same arithmetic
+            // and summation order as logrho_kernel (stages.cu), so both give the same bits.
+            T sum = (T)0;
+#pragma unroll 1
+            for (int m = 0; m < K; m++) sum += KS::dist(hk.ld(m * 32 + lane));
+            const i64 orow = p.link_by_position ? (i64)ql64 * LEAF + lane : (i64)my_id;
+            ((T*)p.logrho_out)[orow] = al_raw_logrho<T>(sum, KS::dist(hk.ld((K - 1) * 32 + lane)), K, p.half_d);
+        }
     } else if (p.row_order == 1) {
 #pragma unroll 1
         for (int m = 0; m < K; m++) {
             if (p.idx_out != nullptr) p.idx_out[pos_row * K + m] = 0xffffffffu;
-            ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>();
+            if (p.d2_out != nullptr) ((T*)p.d2_out)[pos_row * K + m] = inf_t<T>();
         }
     }
     if (p.link_out != nullptr && p.link_by_position) {

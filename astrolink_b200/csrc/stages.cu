@@ -172,9 +172,11 @@ __global__ void __launch_bounds__(256) logrho_kernel(const T* __restrict__ d2, c
         } else {
             for (int j = 0; j < k; j++) s += r[j];
         }
-        v = ((double)k - (double)(T)(s / coreT)) / pow(core, half_d);
+        out[orow] = al_raw_logrho<T>(s, coreT, k, half_d);
+        return;
     } else {
         const u32* ir = idx + i * k;
+        if (ir[0] == 0xffffffffu) return;      // padding row of the last leaf (position-ordered launches): no neighbours
         double sw = 0.0, swd = 0.0;
         for (int j = 0; j < k; j++) {
             const double w = weights[ir[j]];

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __res
 // one warp per leaf: gather the leaf's points into its tile
 template <typename T>
 __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restrict__ P, u32* perm, char* tiles,
-                                                               T* box_lo, T* box_hi, IndexHeader h) {
+                                                               T* box0, IndexHeader h) {
     int lane = threadIdx.x & 31;
     i64 leaf = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (leaf >= h.n_leaves) return;
@@ -402,30 +402,32 @@ __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restri
         if (lane == 0) {
             hdr[j] = a;
             hdr[d + j] = b;
-            box_lo[(i64)j * h.n_leaves + leaf] = a;
-            box_hi[(i64)j * h.n_leaves + leaf] = b;
+            box0[leaf * h.box_stride + 2 * j] = a;
+            box0[leaf * h.box_stride + 2 * j + 1] = b;
         }
     }
+    // padding elements of the box row are defined too
+    if (lane == 0)
+        for (int e = 2 * d; e < h.box_stride; e++) box0[leaf * h.box_stride + e] = (T)0;
     // zero the padding elements of the pair block so the tile is fully defined
     for (int e = 2 * d + half; e < h.pair_block; e += 2) coords[pb * h.pair_block + e] = (T)0;
 }
 
 template <typename T>
-__global__ void tree_build_level_kernel(const T* __restrict__ clo, const T* __restrict__ chi, i64 n_child,
-                                        T* plo, T* phi, i64 n_parent, int d) {
+__global__ void tree_build_level_kernel(const T* __restrict__ cbox, i64 n_child, T* pbox, i64 n_parent, int d, int bs) {
     i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_parent * d) return;
-    i64 node = t % n_parent;
-    int j = (int)(t / n_parent);
+    if (t >= n_parent * bs) return;
+    const i64 node = t / bs;
+    const int e = (int)(t - node * bs);      // element of the box row: 2j = lo_j, 2j + 1 = hi_j, then padding
+    if (e >= 2 * d) { pbox[t] = (T)0; return; }
+    const bool is_hi = e & 1;
     i64 c0 = node * FANOUT, c1 = c0 + FANOUT < n_child ? c0 + FANOUT : n_child;
-    T a = (T)INFINITY, b = -(T)INFINITY;
+    T r = is_hi ? -(T)INFINITY : (T)INFINITY;
     for (i64 c = c0; c < c1; c++) {
-        T x = clo[(i64)j * n_child + c], y = chi[(i64)j * n_child + c];
-        a = x < a ? x : a;
-        b = y > b ? y : b;
+        const T x = cbox[c * bs + e];
+        r = is_hi ? (x > r ? x : r) : (x < r ? x : r);
     }
-    plo[(i64)j * n_parent + node] = a;
-    phi[(i64)j * n_parent + node] = b;
+    pbox[t] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -559,21 +561,16 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
         AL_CHECK_LAUNCH();
     }
 
-    const int eb = (int)sizeof(T);
-    T* lo0 = (T*)(base + h.box_off[0]);
-    T* hi0 = lo0 + (i64)d * h.count[0];
-    tree_build_tiles_kernel<T><<<(unsigned)((n_leaves * 32 + 255) / 256), 256, 0, st>>>(P, perm, base + h.tiles_off, lo0, hi0, h);
+    T* box0 = (T*)(base + h.box_off[0]);
+    tree_build_tiles_kernel<T><<<(unsigned)((n_leaves * 32 + 255) / 256), 256, 0, st>>>(P, perm, base + h.tiles_off, box0, h);
     AL_CHECK_LAUNCH();
     for (int l = 1; l <= h.n_levels; l++) {
-        T* clo = (T*)(base + h.box_off[l - 1]);
-        T* chi = clo + (i64)d * h.count[l - 1];
-        T* plo = (T*)(base + h.box_off[l]);
-        T* phi = plo + (i64)d * h.count[l];
-        i64 work = h.count[l] * d;
-        tree_build_level_kernel<T><<<(unsigned)((work + 127) / 128), 128, 0, st>>>(clo, chi, h.count[l - 1], plo, phi, h.count[l], d);
+        const T* cbox = (const T*)(base + h.box_off[l - 1]);
+        T* pbox = (T*)(base + h.box_off[l]);
+        const i64 work = h.count[l] * h.box_stride;
+        tree_build_level_kernel<T><<<(unsigned)((work + 127) / 128), 128, 0, st>>>(cbox, h.count[l - 1], pbox, h.count[l], d, h.box_stride);
         AL_CHECK_LAUNCH();
     }
-    (void)eb;
     AL_CUDA(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     AL_CUDA(cudaStreamSynchronize(st));
     index_register(index, h);

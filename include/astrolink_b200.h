@@ -107,6 +107,16 @@ int al_knn_dealt(const void* index, int64_t pos_begin, int64_t pos_end, int64_t 
                  int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
                  unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
 
+/* a3 + a4 in one launch (astrolink.py:279 and :293-297): as al_knn_dealt, and additionally the unweighted raw
+ * log-density of every query -- the value al_logrho computes from the same distance row, bit for bit -- is written
+ * from the search epilogue while the sorted distances are still in shared memory: logrho_out[original index] (or
+ * [index position] for dealt launches, like link_out; may be peer-mapped).  With logrho_out given, d2_out may be
+ * NULL: the [rows][k] distance array (the largest output of the search) is then never written.  logrho_out == NULL:
+ * identical to al_knn_dealt.  The weighted density (a5) needs the neighbour ids and stays in al_logrho. */
+int al_knn_density(const void* index, int64_t pos_begin, int64_t pos_end, int64_t chunk_positions, int64_t stride_positions,
+                   int k, int row_order, uint32_t* idx_out, void* d2_out, uint32_t* link_out, int link_cols,
+                   void* logrho_out, int d_intrinsic, unsigned long long* pairs_evaluated, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- a4/a5: _compute_logRho_njit / _compute_weighted_logRho_njit
  *      (astrolink.py:293-303, gather of weights[indices] at :283) ----------
  * out[i] = log((sum_j w_j - sum_j w_j d2[i][j] / d2[i][k-1]) / d2[i][k-1]^(d_intrinsic/2)),

@@ -199,6 +199,69 @@ def test_knn_dealt_launches_equal_one_launch(n, d, world, chunk_leaves):
     assert (raw == raw_ref).all()
 
 
+@pytest.mark.parametrize("n,d,dtype,k,d_int", [(30011, 6, np.float32, 20, 6), (20000, 3, np.float32, 20, 2), (9000, 2, np.float64, 9, 2),
+                                               (5000, 8, np.float64, 33, 8), (33, 3, np.float32, 5, 3), (7000, 16, np.float32, 25, 5)])
+def test_fused_density_equals_separate_pass(n, d, dtype, k, d_int):
+    """al_knn_density (a3 + a4 in one launch, astrolink.py:279 and :293-297): the raw log-density written by the search
+    epilogue equals al_logrho of the same distance rows bit for bit -- by original index, and by index position for
+    dealt launches -- and with d2_out == NULL nothing else changes."""
+    from astrolink_b200 import dist as adist
+    nat = _native()
+    rng = np.random.default_rng(7 * n + d)
+    P = np.concatenate([rng.normal(0, 1, (n // 2, d)), rng.normal(2, 0.1, (n - n // 2, d))]).astype(dtype)
+    index = nat.Index(_cu(P))
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    L = min(7, k)
+    d2_ref, idx_ref = index.knn(k)
+    raw_ref = nat.logrho(d2_ref, idx_ref, k, d_int)
+    # fused, by original index, distance rows still written
+    link = torch.full((n, L), -7, dtype=torch.int32, device="cuda")
+    raw = torch.full((n,), float("nan"), dtype=tdt, device="cuda")
+    d2, idx = index.knn(k, link_out=link, logrho_out=raw, d_intrinsic=d_int)
+    assert (d2 == d2_ref).all() and (idx == idx_ref).all() and (link == idx_ref[:, :L]).all()
+    assert (raw.view(torch.int32 if dtype == np.float32 else torch.int64) ==
+            raw_ref.view(torch.int32 if dtype == np.float32 else torch.int64)).all(), "fused density must equal al_logrho bit for bit"
+    # fused, no distance rows, no index rows
+    link2 = torch.full((n, L), -7, dtype=torch.int32, device="cuda")
+    raw2 = torch.full((n,), float("nan"), dtype=tdt, device="cuda")
+    d2n, idxn = index.knn(k, link_out=link2, want_idx=False, logrho_out=raw2, d_intrinsic=d_int, want_d2=False)
+    assert d2n is None and idxn is None and (link2 == link).all() and (raw2 == raw_ref).all()
+    # dealt launches: densities by index position
+    positions = index.positions
+    knn_pos = torch.full((positions, L), -5, dtype=torch.int32, device="cuda")
+    raw_pos = torch.full((positions,), float("nan"), dtype=tdt, device="cuda")
+    for r in range(3):
+        begin, chunk, stride, rows = adist.deal_chunks(positions, r, 3, nat.LEAF, 8)
+        index.knn(k, pos_begin=begin, pos_end=positions, row_order=1, link_out=knn_pos, want_idx=False, chunk=chunk, stride=stride,
+                  logrho_out=raw_pos, d_intrinsic=d_int, want_d2=False)
+    raw3 = torch.full((n,), float("nan"), dtype=tdt, device="cuda")
+    kNN3 = torch.full((n, L), -9, dtype=torch.int32, device="cuda")
+    nat.scatter_rows(raw_pos.view(-1, 1), index.perm(), raw3.view(-1, 1))
+    nat.scatter_rows(knn_pos, index.perm(), kNN3)
+    torch.cuda.synchronize()
+    assert (raw3 == raw_ref).all() and (kNN3 == idx_ref[:, :L]).all()
+
+
+def test_weighted_density_skips_padding_rows():
+    """Position-ordered launches (multi-GPU path) fill the padding rows of the last leaf with 0xffffffff ids; the weighted
+    density (a5, astrolink.py:299-303) must not gather weights through them (n % 32 != 0)."""
+    nat = _native()
+    n, d, k = 1003, 3, 12
+    rng = np.random.default_rng(5)
+    P = rng.normal(size=(n, d)).astype(np.float32)
+    w = torch.from_numpy(rng.uniform(0.5, 2.0, n)).cuda()
+    index = nat.Index(_cu(P))
+    d2, idx = index.knn(k, row_order=1)
+    assert d2.shape[0] == index.positions and index.positions > n
+    raw = nat.logrho(d2, idx, k, d, weights=w)
+    d2o, idxo = index.knn(k)
+    raw_o = nat.logrho(d2o, idxo, k, d, weights=w)
+    perm = index.perm().cpu().numpy()
+    torch.cuda.synchronize()
+    got = raw.cpu().numpy()[perm >= 0]
+    assert (got == raw_o.cpu().numpy()[perm[perm >= 0]]).all()
+
+
 @pytest.mark.parametrize("L,stride,dtype", [(7, 7, np.float32), (7, 20, np.float32), (9, 9, np.float64), (2, 2, np.float32),
                                             (18, 18, np.float32), (40, 40, np.float64)])
 def test_make_edges_layouts_vs_oracle(L, stride, dtype):
