@@ -13,12 +13,18 @@ __global__ void __launch_bounds__(256) agg_kernel(i64 n, F f) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) f(i);
 }
 
+// the same, skipped as a whole when *flag == 0 (flag == nullptr: always runs)
+template <class Tag, class F>
+__global__ void __launch_bounds__(256) agg_kernel_if(const u32* flag, i64 n, F f) {
+    if (flag != nullptr && *flag == 0u) return;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) f(i);
+}
+
 __global__ void agg_fill_kernel(u32* p, u32 v, i64 n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__global__ void agg_save_last_kernel(const u32* last_in, u32* tot) { tot[0] = *last_in; }
-__global__ void agg_total_kernel(const u32* last_out, u32* tot) { tot[1] = *last_out + tot[0]; }
+__global__ void agg_total_kernel(const u32* last_in, const u32* last_out, u32* tot) { tot[0] = *last_in + *last_out; }
 
 // Everything runs on one stream, so workspace released with ar.reset() may be handed to the next
 // kernel without a host synchronisation: stream order already separates the two uses.
@@ -26,6 +32,7 @@ struct CudaExec {
     cudaStream_t st;
     cudaError_t err = cudaSuccess;
     long launches = 0;
+    long reads = 0;
 
     void note(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
 
@@ -35,6 +42,15 @@ struct CudaExec {
         i64 g = (n + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
         agg_kernel<Tag, F><<<(unsigned)g, 256, 0, st>>>(n, f);
+        note(cudaGetLastError());
+        launches++;
+    }
+    template <class Tag, class F>
+    void launch_if(const u32* flag, i64 n, F f) {
+        if (n <= 0) return;
+        i64 g = (n + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        agg_kernel_if<Tag, F><<<(unsigned)g, 256, 0, st>>>(flag, n, f);
         note(cudaGetLastError());
         launches++;
     }
@@ -48,31 +64,26 @@ struct CudaExec {
             note(cudaGetLastError());
         }
     }
-    u32 read_u32(const u32* p) {
-        u32 v = 0;
-        note(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, st));
+    // one blocking read of `count` consecutive device words (the only host round trips of the pass)
+    void read_u32s(const u32* p, u32* host, int count) {
+        note(cudaMemcpyAsync(host, p, 4 * (size_t)count, cudaMemcpyDeviceToHost, st));
         note(cudaStreamSynchronize(st));
-        return v;
+        reads++;
     }
-    // out[i] = sum of in[0..i); returns the total
-    i64 exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar) {
-        if (n <= 0) return 0;
+    // out[i] = sum of in[0..i); the total goes to total_dev[0] on the device (no host synchronisation).  `out` must
+    // not alias `in`.
+    void exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar, u32* total_dev) {
+        if (n <= 0) { note(cudaMemsetAsync(total_dev, 0, 4, st)); return; }
         const size_t mk = ar.mark();
         size_t tb = 0;
         note(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, st));
         void* tmp = ar.get<char>(tb);
-        if (!ar.ok) { ar.reset(mk); return -1; }
-        u32* tot = ar.get<u32>(2);
-        if (!ar.ok) { ar.reset(mk); return -1; }
-        // the last input is saved before the scan (`out` may alias `in`); one device-side add, one host read
-        agg_save_last_kernel<<<1, 1, 0, st>>>(in + (n - 1), tot);
+        if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, st));
-        agg_total_kernel<<<1, 1, 0, st>>>(out + (n - 1), tot);
+        agg_total_kernel<<<1, 1, 0, st>>>(in + (n - 1), out + (n - 1), total_dev);
         note(cudaGetLastError());
-        launches += 2;
-        const u32 total = read_u32(tot + 1);
+        launches += 1;
         ar.reset(mk);
-        return (i64)total;
     }
     void inclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena& ar) {
         if (n <= 0) return;
@@ -136,7 +147,7 @@ struct CudaExec {
         if (!prof) return;
         cudaStreamSynchronize(st);
         double t = now();
-        if (cur) fprintf(stderr, "[al_aggregate] %-36s %8.3f ms  (launches so far %ld)\n", cur, t - t0, launches);
+        if (cur) fprintf(stderr, "[al_aggregate] %-36s %8.3f ms  (launches so far %ld, host reads %ld)\n", cur, t - t0, launches, reads);
         static char keep[64];
         snprintf(keep, sizeof(keep), "%s", name);
         cur = keep;

@@ -183,8 +183,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         for (int it = 0; it < 7; it++) {
             const u32* prev = it > 0 ? changed + (it - 1) : nullptr;
             u32* cur = changed + it;
-            x.template launch<TagJump>(N, AGG_LAMBDA(i64 s) {
-                if (prev != nullptr && agg_load_relaxed(prev) == 0u) return;
+            x.template launch_if<TagJump>(prev, N, AGG_LAMBDA(i64 s) {
                 u32 h = agg_load_relaxed(hook + s);
                 const u32 h0 = h;
                 bool at_root = false;

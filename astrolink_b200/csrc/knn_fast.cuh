@@ -35,6 +35,12 @@
 #ifndef KF_QCAP
 #define KF_QCAP 8
 #endif
+#ifndef KF_OPEN2
+#define KF_OPEN2 1             // box tests: two needy queries per iteration (two independent chains)
+#endif
+#ifndef KF_SPARSE4
+#define KF_SPARSE4 1           // sparse tiles: two passes (four needy queries) in flight per iteration
+#endif
 
 namespace kf {
 
@@ -151,8 +157,9 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
     const u32 queue_sa = tile_sa + 2u * G::TS + (u32)lane * 8u;            // this lane's queue slot 0 (slot stride 256)
     const u32 root_sa = tile_sa + 2u * G::TS + QC * 256u + (u32)lane * 8u; // this lane's heap root
     const u32 pair_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)lane * 16u;     // this lane's pair 0 (pair stride 512)
-    const u32 qt_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)NP * 512u;        // query table
-    const u32 qbox_sa = qt_sa + 33u * G::RS * 4u;                          // own leaf's box, (lo_j, hi_j) pairs
+    // query table: row -1 is a dummy query nothing is near to (the partner of the last query of an odd sparse pass)
+    const u32 qt_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)NP * 512u + G::RS * 4u;
+    const u32 qbox_sa = qt_sa + 32u * G::RS * 4u;                          // own leaf's box, (lo_j, hi_j) pairs
     const u32 need_sa = qbox_sa + G::BS * 4u;                              // [n_levels + 1][32] need masks
     const u32 stk_sa = need_sa + (u32)(n_levels + 1) * 128u;               // stack: mask[8] | node[8] | level[8]
     const u32 bar_sa = stk_sa + 3u * MAX_WIDE_LEVELS * 4u;                 // 2 mbarriers
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the dummy query of an odd sparse pass: nothing is within distance -1 of it
 #pragma unroll
-        for (int j = 0; j < G::RS; j++) stsf(qt_sa + 32u * G::RS * 4u + 4u * j, j == D ? -1.f : 0.f);
+        for (int j = 0; j < G::RS; j++) stsf(qt_sa - G::RS * 4u + 4u * j, j == D ? -1.f : 0.f);
     }
     sts64(root_sa, kinf);
 #pragma unroll 1
@@ -252,13 +259,10 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         u32 mask = 0;
         if (__any_sync(FULL, pass)) {
             u32 m = qmask;
-#pragma unroll 1
-            while (m) {
-                const u32 lb = m & (0u - m);        // lowest needy query, as a bit
-                m ^= lb;
-                const int qi = 31 - __clz(lb);
+            // distance from query row `qi` to this lane's child box
+            auto box_dist = [&](int qi, float& kth) -> float {
                 float row[G::RS];
-                load_qrow<D>(qt_sa + (u32)qi * (G::RS * 4u), row);
+                load_qrow<D>(qt_sa + (u32)(qi * (G::RS * 4)), row);
                 float pd = 0.f;
 #pragma unroll
                 for (int j = 0; j < D; j++) {
@@ -267,9 +271,36 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                     const float g = fmaxf(fmaxf(-a, b), 0.f);
                     pd = __fmaf_rn(g, g, pd);
                 }
-                if (pd <= row[D]) mask |= lb;
+                kth = row[D];
+                return pd;
+            };
+#if KF_OPEN2
+#pragma unroll 1
+            while (m) {
+                // two needy queries per iteration (independent chains); an odd count pairs the last one with the dummy
+                // query (row -1, k-th distance -1: never needed)
+                const u32 ba = m & (0u - m);
+                m ^= ba;
+                const u32 bb = m & (0u - m);
+                m ^= bb;
+                float ka, kb;
+                const float pa = box_dist(31 - __clz(ba), ka);
+                const float pb = box_dist(31 - __clz(bb), kb);
+                if (pa <= ka) mask |= ba;
+                if (pb <= kb) mask |= bb;
                 if (KNN_STATS) st_open_iter++;
             }
+#else
+#pragma unroll 1
+            while (m) {
+                const u32 lb = m & (0u - m);        // lowest needy query, as a bit
+                m ^= lb;
+                float kth;
+                const float pd = box_dist(31 - __clz(lb), kth);
+                if (pd <= kth) mask |= lb;
+                if (KNN_STATS) st_open_iter++;
+            }
+#endif
             mask = pass ? mask : 0u;
         }
         sts32(out_sa + 4u * lane, mask);
@@ -365,91 +396,131 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         }
     };
 
-    // distances from the queries in `need` to the 32 candidates of the tile in buffer `bw`
-    auto eval_tile = [&](u32 bw, u32 need) {
+    // ---- dense: every lane evaluates all 32 candidates of the tile in buffer `bw`, two per instruction (packed f32x2,
+    // broadcast tile reads)
+    auto eval_dense = [&](u32 bw) {
         const u32 coords_sa = tile_sa + bw * (u32)G::TS + (u32)G::HDR;
         const u32 ids_sa = tile_sa + bw * (u32)G::TS + (u32)G::IDS;
-        const int n_need = __popc(need);
-        if (KNN_BRUTE || n_need > KF_SPARSE_MAX) {
-            // ---- dense: every lane evaluates all 32 candidates, two per instruction (packed f32x2, broadcast tile reads)
-            if (KNN_STATS) st_dense++;
-            n_qt += 32;
-            if (__any_sync(FULL, cnt > QC - 4)) flush();        // the sparse path can leave queues fuller than a chunk allows
+        if (KNN_STATS) st_dense++;
+        n_qt += 32;
+        if (__any_sync(FULL, cnt > QC - 4)) flush();        // the sparse path can leave queues fuller than a chunk allows
 #pragma unroll 1
-            for (int pb0 = 0; pb0 < LEAF / 2; pb0 += 2) {
-                float v[4];
+        for (int pb0 = 0; pb0 < LEAF / 2; pb0 += 2) {
+            float v[4];
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    u64 acc = 0ull;
-#pragma unroll
-                    for (int v4 = 0; v4 < G::PB4; v4++) {
-                        const float4 f = lds_f4(coords_sa + (u32)((pb0 + c) * G::PB4 + v4) * 16u);
-                        if (2 * v4 < D) {
-                            const u64 df = sub2(pack2(q[2 * v4], q[2 * v4]), pack2(f.x, f.y));
-                            acc = fma2(df, df, acc);
-                        }
-                        if (2 * v4 + 1 < D) {
-                            const u64 df = sub2(pack2(q[2 * v4 + 1], q[2 * v4 + 1]), pack2(f.z, f.w));
-                            acc = fma2(df, df, acc);
-                        }
-                    }
-                    unpack2(acc, v[2 * c], v[2 * c + 1]);
-                }
-                const float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
-                if (__any_sync(FULL, mn <= worst)) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        if (v[e] <= worst) {
-                            sts64(queue_sa + (u32)cnt * 256u, make_key(v[e], lds32(ids_sa + (u32)(2 * pb0 + e) * 4u)));
-                            cnt++;
-                            if (KNN_STATS) st_push++;
-                        }
-                    }
-                    if (__any_sync(FULL, cnt > QC - 4)) flush();
-                }
-            }
-        } else if (n_need > 0) {
-            // ---- sparse: each half-warp holds the whole tile (lane l and l + 16: candidates 2 (l & 15) and 2 (l & 15) + 1 as
-            // packed pairs, exactly the tile's pair block), the lower half evaluates one needy query, the upper half another
-            n_qt += n_need;
-            const u32 hl = (u32)lane & 15u;
-            u64 cand[D + 1];
-#pragma unroll
-            for (int v4 = 0; v4 < G::PB4; v4++) {
-                const float4 f = lds_f4(coords_sa + hl * (G::PB * 4u) + 16u * v4);
-                if (2 * v4 < D) cand[2 * v4] = pack2(f.x, f.y);
-                if (2 * v4 + 1 < D) cand[2 * v4 + 1] = pack2(f.z, f.w);
-            }
-            u32 id0, id1;
-            lds32x2(ids_sa + hl * 8u, id0, id1);
-            u32 m = need;
-#pragma unroll 1
-            while (m) {
-                const int qa = __ffs(m) - 1;
-                m &= m - 1;
-                const int qb = m ? __ffs(m) - 1 : 32;       // odd count: the upper half takes the dummy query
-                m &= m - 1;
-                const int myq = lane < 16 ? qa : qb;
-                float row[G::RS];
-                load_qrow<D>(qt_sa + (u32)myq * (G::RS * 4u), row);
+            for (int c = 0; c < 2; c++) {
                 u64 acc = 0ull;
 #pragma unroll
-                for (int j = 0; j < D; j++) {
-                    const u64 df = sub2(pack2(row[j], row[j]), cand[j]);
-                    acc = fma2(df, df, acc);
+                for (int v4 = 0; v4 < G::PB4; v4++) {
+                    const float4 f = lds_f4(coords_sa + (u32)((pb0 + c) * G::PB4 + v4) * 16u);
+                    if (2 * v4 < D) {
+                        const u64 df = sub2(pack2(q[2 * v4], q[2 * v4]), pack2(f.x, f.y));
+                        acc = fma2(df, df, acc);
+                    }
+                    if (2 * v4 + 1 < D) {
+                        const u64 df = sub2(pack2(q[2 * v4 + 1], q[2 * v4 + 1]), pack2(f.z, f.w));
+                        acc = fma2(df, df, acc);
+                    }
                 }
-                float d0, d1;
-                unpack2(acc, d0, d1);
-                const bool h0 = d0 <= row[D], h1 = d1 <= row[D];
-                if (__any_sync(FULL, h0 || h1)) {       // the common pass has no hit at all: one vote, one branch
-                    const u32 b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
-                    emit(b0 & 0xffffu, d0, id0, qa, 0);
-                    emit(b1 & 0xffffu, d1, id1, qa, 0);
-                    emit(b0 >> 16, d0, id0, qb, 16);
-                    emit(b1 >> 16, d1, id1, qb, 16);
+                unpack2(acc, v[2 * c], v[2 * c + 1]);
+            }
+            const float mn = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
+            if (__any_sync(FULL, mn <= worst)) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (v[e] <= worst) {
+                        sts64(queue_sa + (u32)cnt * 256u, make_key(v[e], lds32(ids_sa + (u32)(2 * pb0 + e) * 4u)));
+                        cnt++;
+                        if (KNN_STATS) st_push++;
+                    }
                 }
+                if (__any_sync(FULL, cnt > QC - 4)) flush();
             }
         }
+    };
+
+    // ---- sparse: each half-warp holds the whole tile (lanes l and l + 16: candidates 2 (l & 15) and 2 (l & 15) + 1 as
+    // packed pairs, exactly the tile's pair block, in `c4`); the lower half evaluates one needy query, the upper half another.
+    // `ids_of` yields this lane's two candidate ids; it is only called when a pass has a hit.
+    const u32 hl = (u32)lane & 15u;
+    auto eval_sparse = [&](const float4* c4, u32 need, auto ids_of) {
+        n_qt += __popc(need);
+        u64 cand[D + 1];
+#pragma unroll
+        for (int v4 = 0; v4 < G::PB4; v4++) {
+            if (2 * v4 < D) cand[2 * v4] = pack2(c4[v4].x, c4[v4].y);
+            if (2 * v4 + 1 < D) cand[2 * v4 + 1] = pack2(c4[v4].z, c4[v4].w);
+        }
+        u32 m = need;
+        // one pass: the lower half-warp evaluates the query of bit `ba`, the upper half the query of bit `bb` (0: the dummy
+        // query, row -1, whose k-th distance is -1) against this lane's two candidates
+        auto pass_dist = [&](u32 ba, u32 bb, float& d0, float& d1, float& kth) {
+            const int myq = 31 - __clz(lane < 16 ? ba : bb);
+            float row[G::RS];
+            load_qrow<D>(qt_sa + (u32)(myq * (G::RS * 4)), row);
+            u64 acc = 0ull;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const u64 df = sub2(pack2(row[j], row[j]), cand[j]);
+                acc = fma2(df, df, acc);
+            }
+            unpack2(acc, d0, d1);
+            kth = row[D];
+        };
+        auto pass_hits = [&](u32 ba, u32 bb, float d0, float d1, bool h0, bool h1) {
+            const u32 b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
+            if ((b0 | b1) == 0u) return;
+            u32 id0, id1;
+            ids_of(id0, id1);
+            const int qa = 31 - __clz(ba), qb = 31 - __clz(bb);
+            emit(b0 & 0xffffu, d0, id0, qa, 0);
+            emit(b1 & 0xffffu, d1, id1, qa, 0);
+            emit(b0 >> 16, d0, id0, qb, 16);        // no hits when bb == 0
+            emit(b1 >> 16, d1, id1, qb, 16);
+        };
+#if KF_SPARSE4
+#pragma unroll 1
+        while (m) {
+            // two passes (up to four needy queries) per iteration: two independent load + FMA chains in flight
+            const u32 ba = m & (0u - m);
+            m ^= ba;
+            const u32 bb = m & (0u - m);
+            m ^= bb;
+            const u32 bc = m & (0u - m);
+            m ^= bc;
+            const u32 bd = m & (0u - m);
+            m ^= bd;
+            float d0, d1, k0, e0, e1, k1;
+            pass_dist(ba, bb, d0, d1, k0);
+            pass_dist(bc, bd, e0, e1, k1);        // bc == bd == 0: both halves take the dummy query
+            const bool h0 = d0 <= k0, h1 = d1 <= k0, g0 = e0 <= k1, g1 = e1 <= k1;
+            if (__any_sync(FULL, h0 || h1 || g0 || g1)) {       // the common iteration has no hit at all: one vote, one branch
+                pass_hits(ba, bb, d0, d1, h0, h1);
+                pass_hits(bc, bd, e0, e1, g0, g1);
+            }
+        }
+#else
+#pragma unroll 1
+        while (m) {
+            const u32 ba = m & (0u - m);
+            m ^= ba;
+            const u32 bb = m & (0u - m);
+            m ^= bb;
+            float d0, d1, k0;
+            pass_dist(ba, bb, d0, d1, k0);
+            const bool h0 = d0 <= k0, h1 = d1 <= k0;
+            if (__any_sync(FULL, h0 || h1)) pass_hits(ba, bb, d0, d1, h0, h1);
+        }
+#endif
+    };
+    // the same from the tile in shared-memory buffer `bw`
+    auto eval_sparse_smem = [&](u32 bw, u32 need) {
+        const u32 coords_sa = tile_sa + bw * (u32)G::TS + (u32)G::HDR;
+        const u32 ids_sa = tile_sa + bw * (u32)G::TS + (u32)G::IDS;
+        float4 c4[G::PB4];
+#pragma unroll
+        for (int v4 = 0; v4 < G::PB4; v4++) c4[v4] = lds_f4(coords_sa + hl * (G::PB * 4u) + 16u * v4);
+        eval_sparse(c4, need, [&](u32& id0, u32& id1) { lds32x2(ids_sa + hl * 8u, id0, id1); });
     };
 
     // ---- own leaf (tile 0, no look-ahead: the box tests need the queries and their first bounds)
@@ -466,7 +537,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         worst = my_id != 0xffffffffu ? INFINITY : -1.f;
         stsf(myrow_sa + 4u * D, worst);
         __syncwarp();
-        eval_tile(0u, FULL);
+        eval_dense(0u);
     }
     // ---- the other leaves: while tile t is evaluated, the traversal has already found tile t + 1 and its copy is in flight
     int cur = next_candidate();
@@ -483,7 +554,8 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 issue_tile(nxt, (t & 1u) ^ 1u);
             }
             wait_tile(t);
-            eval_tile(t & 1u, cur_need);
+            if (KNN_BRUTE || __popc(cur_need) > KF_SPARSE_MAX) eval_dense(t & 1u);
+            else eval_sparse_smem(t & 1u, cur_need);
             if (nxt < 0) break;
             cur_need = nxt_need;
             t++;

@@ -37,6 +37,37 @@ import numpy as np  # noqa: E402
 
 METRIC = "points/sec for full run() (10M pts, 6D)"
 UNIT = "points/s"
+CPU_SAMPLE = 2000000        # the SAME fixed prefix of the shuffled cloud on every box and in both CPU legs
+
+
+def full_config_extrapolation():
+    """What the CPU legs would read on the whole workload instead of the fixed sample: committed full-size timings."""
+    out = {"note": "kNN cost per point grows with n, so the fixed-sample rate overstates the CPU path; these are full-C4 timings"}
+    try:
+        r = json.load(open(os.path.join(ROOT, "profiles", "r01_fullscale_parity.json")))["C4"]
+        sec = r["oracle_knn_s"] + r["oracle_aggregate_s"]
+        out["oracle_port_full_c4"] = {"points_per_s": 1e7 / sec, "seconds": sec, "cores": 16,
+                                      "source": "profiles/r01_fullscale_parity.json (kNN + aggregate of the C port on all 10M points, one B200 box)"}
+    except Exception:
+        pass
+    try:
+        r = json.load(open(os.path.join(ROOT, "profiles", "r02_reference_numba_cpu.json")))
+        c4 = r["runs"]["C4"]
+        out["reference_numba_full_c4"] = {"points_per_s": c4["points_per_s"], "seconds": c4["total_s"], "cores": r["machine_cores"],
+                                          "source": "profiles/r02_reference_numba_cpu.json (the reference's own numba stages, cKDTree stand-in "
+                                                    "for pykdtree, build container)"}
+    except Exception:
+        pass
+    return out
+
+
+def result_checksum(c):
+    """64-bit digest of the results a user reads; equal at every N if and only if the sharded runs reproduce N=1."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=8)
+    for a in (c.ordering, c.groups, c.clusters, c.logRho):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
 
 
 def parse_args():
@@ -46,7 +77,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", help="C4 (default, 10M x 6D) or C2/C3 or n=<points> for a reduced halo")
-    ap.add_argument("--cpu-sample", type=int, default=3000000, help="points in the cpu_baseline sample (about 10-30 s of CPU work)")
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE, help="points of the fixed CPU sample (cpu_baseline and --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -176,13 +207,8 @@ def run_reference(args):
     oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
     P, kwargs, desc = make_workload(args.workload)
     n_s = min(args.cpu_sample, P.shape[0])
-    # warm-up on a small prefix; its rate sizes the per-step sample so that K steps stay within about three minutes
-    n_w = max(20000, n_s // 20)
-    t_w = 0.0
-    for _ in range(max(1, min(args.warmup, 1))):
-        t_w, _ = cpu_hot_path_seconds(np.ascontiguousarray(P[:n_w]), kwargs)
-    if t_w > 0:
-        n_s = int(max(min(n_s, 200000), min(n_s, 180.0 / max(1, args.steps) * (n_w / t_w))))
+    # one warm-up on a small prefix (pages the library in); the timed sample is the same fixed prefix on every box
+    cpu_hot_path_seconds(np.ascontiguousarray(P[:20000]), kwargs)
     sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
     times = []
     stage = None
@@ -196,7 +222,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "sample": f"first {n_s} points of the shuffled cloud per step"},
+        "config": {"workload": f"{args.workload}: {desc}", "sample": f"first {n_s} points of the shuffled cloud per step (fixed size)"},
+        "full_config_extrapolation": full_config_extrapolation(),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n_s}-point prefix of the workload; oracle C port (OpenMP kNN, serial aggregate) + Python host stats; "
                                    f"stage seconds {json.dumps({k: round(v, 3) for k, v in stage.items()})}"},
@@ -296,6 +323,7 @@ def run_b200(args):
     host_timers = {k: round(1e3 * getattr(c, k), 2) for k in ("_transformTime", "_logRhoTime", "_aggregateTime", "_regrTime", "_rejTime", "_totalTime")}
     K, L = c.k_den, c.k_link
     n_groups, n_clusters = (int(c.groups.shape[0]), int(c.clusters.shape[0])) if rank == 0 else (0, 0)
+    checksum = result_checksum(c) if rank == 0 else None
     c = None                                  # release its buffers before the e2e series
     ms_e2e, c2, _, steps_e2e = timed(False, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -316,9 +344,9 @@ def run_b200(args):
             td.destroy_process_group()
         return 0
     fp32_peak = nat.fp32_peak_tflops()
-    traffic = None          # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    traffic = None          # dram bytes per launch of the dominant kernel, from this round's committed ncu --set full capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_knn_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_knn_traffic.json")))
         if args.workload == "C4" and world == 1:
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
@@ -332,37 +360,66 @@ def run_b200(args):
     flops = pairs * 3.0 * d                      # this rank's launch
     achieved = flops / (stage["knn"] * 1e-3) / 1e12
     E = n * (L - 1)
-    esz = 4
+    esz = P.dtype.itemsize
+    tile_bytes = 32 * 4 + 16 * ((2 * d + 3) // 4 * 4) * esz + (2 * d * esz + 15) // 16 * 16
     hbm = {   # algorithmic bytes per launch (DESIGN.md "Kernels")
-        "density": n * K * esz + n * esz,
+        "rescale": 4 * n * d * esz,                                       # mean pass, variance pass, apply: 3 reads + 1 write
+        "index_build": n * d * esz + (n // 32) * ((tile_bytes + 127) // 128 * 128) + n * 4,   # read P once, write tiles + permutation
         "normalise": 3 * n * esz,
         "edges": n * L * 4 + n * L * esz + n * esz + E * (esz + 8),
         "sort": E * 4 + E * 68 + E * 16,
+        "aggregate": E * 8 + n * esz + n * 4 + n_groups * (12 + 2 * esz),     # read the sorted pairs and logRho once, write ordering + rows
     }
     stages_out = {k: round(v, 3) for k, v in stage.items()}
-    others = {k: {"ms": round(stage[k], 3), "GB/s": round(hbm[k] / (stage[k] * 1e-3) / 1e9, 1),
-                  "frac_of_measured_hbm": round(hbm[k] / (stage[k] * 1e-3) / 1e9 / hbm_peak, 3)} for k in hbm if k in stage}
+    others = {k: {"ms": round(stage[k], 3), "algorithmic_bytes": int(hbm[k]), "GB/s": round(hbm[k] / (stage[k] * 1e-3) / 1e9, 1),
+                  "frac_of_measured_hbm": round(hbm[k] / (stage[k] * 1e-3) / 1e9 / hbm_peak, 3)} for k in hbm if k in stage and stage[k] > 0}
+    # the density pass is fused into the search epilogue; its stand-alone kernel is timed once here for the GB/s evidence
+    try:
+        with torch.cuda.device(dev):
+            dPt, _ = nat.rescale(dP) if kwargs.get("adaptive", 1) else (dP, None)
+            idx_ = nat.Index(dPt)
+            d2_, _i = idx_.knn(K, row_order=0, link_out=torch.empty((n, L), dtype=torch.int32, device=dev), want_idx=False)
+            del idx_, dPt
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            nat.logrho(d2_, None, K, d)
+            ev[0].record()
+            nat.logrho(d2_, None, K, d)
+            ev[1].record()
+            torch.cuda.synchronize(dev)
+            ms_d = ev[0].elapsed_time(ev[1])
+            bytes_d = n * K * esz + n * esz
+            others["density_standalone"] = {"ms": round(ms_d, 3), "algorithmic_bytes": int(bytes_d), "GB/s": round(bytes_d / (ms_d * 1e-3) / 1e9, 1),
+                                            "frac_of_measured_hbm": round(bytes_d / (ms_d * 1e-3) / 1e9 / hbm_peak, 3),
+                                            "note": "al_logrho on the [n, k_den] distance rows, outside the timed region; run() uses the fused epilogue"}
+            del d2_
+    except Exception as e:      # evidence only: never fail the bench line over it
+        others["density_standalone"] = {"error": str(e)[:200]}
 
     h2d = P.nbytes
+    ws_mb = {"P": P.nbytes / 1e6, "index tiles": (n // 32) * ((tile_bytes + 127) // 128 * 128) / 1e6, "edges (keys + pairs)": E * (esz + 8) / 1e6,
+             "kNN link rows": n * L * 4 / 1e6}
+    l2_note = ("inputs larger than L2, no explicit flush: " + ", ".join(f"{k} {v:.0f} MB" for k, v in ws_mb.items()) +
+               f" (sum {sum(ws_mb.values()):.0f} MB) vs 126 MB L2; every step streams all of them and allocates fresh buffers")
     d2h = int(c2.logRho.nbytes + c2.ordering.nbytes + c2.groups.nbytes + c2.prominences.nbytes)
     line = {
         "metric": METRIC, "value": n / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_value, "ms_each_step": steps_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k_den": K, "k_link": L,
                    "parallelism": f"query-sharded x{world}, aggregation on rank 0" if world > 1 else "single GPU",
-                   "l2": "working set (P 240 MB, kNN 1.6 GB, 60M edges) >> 126 MB L2; no flush needed",
+                   "l2": l2_note,
                    "groups": n_groups, "clusters": n_clusters},
+        "result_checksum": checksum,
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "ms_each_step": steps_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(round(launches)),
         "clocks": clocks,
-        "roofline": {"kernel": f"knn_kernel<float,{d}>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "roofline": {"kernel": f"kf::knn_fast_kernel<{d}>" if P.dtype == np.float32 else f"knn_kernel<double,{d}>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                      "pairs_evaluated": pairs, "flop_per_pair": 3 * d, "kernel_ms": stage["knn"],
                      "brute_force_equiv_tflops": (float(n) * n * 3 * d) / (knn_ms * 1e-3) / 1e12 / world,
                      "peak_source": "FP32 FMA issue rate measured in this run (al_fp32_peak_tflops); MEASURED_PEAKS.json has no FP32 figure",
-                     "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak; the kernel is instruction-issue bound "
-                                     "(69% issue-slot utilisation in profiles/r01_knn_c4_ncu_summary.txt): tree pruning and per-query "
-                                     "selection, not distance arithmetic, dominate its instruction stream"},
+                     "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak; the kernel is instruction-issue / latency bound "
+                                     "(profiles/r02_knn_*): tree pruning and per-query selection, not distance arithmetic, dominate its "
+                                     "instruction stream, so a faster kernel evaluates FEWER pairs per second of FP32 peak, not more"},
         "stage_ms": stages_out,
         "knn_ms_over_ranks": {"min": round(knn_ms_min, 3), "max": round(knn_ms, 3)},
         "host_timers_ms": host_timers,
@@ -377,8 +434,9 @@ def run_b200(args):
         cpu_hot_path_seconds(sample[:20000], kwargs)
         sec, st = cpu_hot_path_seconds(sample, kwargs)
         line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                                "sample": f"{n_s}-point prefix of the shuffled workload, one run ({sec:.1f} s); oracle C port "
-                                          f"(OpenMP KD-tree kNN, serial aggregate) + Python host stats"}
+                                "sample": f"fixed {n_s}-point prefix of the shuffled workload, one run ({sec:.1f} s); oracle C port "
+                                          f"(OpenMP KD-tree kNN, serial aggregate) + Python host stats",
+                                "full_config_extrapolation": full_config_extrapolation()}
     _emit(line)
     if D is not None:
         import torch.distributed as td

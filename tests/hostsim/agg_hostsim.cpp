@@ -15,17 +15,36 @@
 
 struct HostExec {
     long launches = 0;
+    // order in which the "threads" of a pass run: 0 ascending, 1 descending, 2 a fixed pseudo-random permutation --
+    // three different valid interleavings of the GPU threads; the passes must not depend on which one they get
+    int order = 0;
     template <class Tag, class F>
     void launch(i64 n, F f) {
-        for (i64 i = 0; i < n; i++) f(i);
+        if (order == 0) {
+            for (i64 i = 0; i < n; i++) f(i);
+        } else if (order == 1) {
+            for (i64 i = n - 1; i >= 0; i--) f(i);
+        } else {
+            // i -> (a * i + b) mod n with a coprime to n visits every index once
+            i64 a = 2654435761ll % (n > 0 ? n : 1);
+            if (a == 0) a = 1;
+            while (std::gcd(a, n) != 1) a++;
+            i64 v = 12345 % (n > 0 ? n : 1);
+            for (i64 i = 0; i < n; i++) { f(v); v += a; if (v >= n) v -= n; }
+        }
         launches++;
     }
+    template <class Tag, class F>
+    void launch_if(const u32* flag, i64 n, F f) {
+        if (flag != nullptr && *flag == 0u) return;
+        launch<Tag>(n, f);
+    }
     void fill_u32(u32* p, u32 v, i64 n) { for (i64 i = 0; i < n; i++) p[i] = v; }
-    u32 read_u32(const u32* p) { return *p; }
-    i64 exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&) {
+    void read_u32s(const u32* p, u32* host, int count) { for (int i = 0; i < count; i++) host[i] = p[i]; }
+    void exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&, u32* total) {
         i64 s = 0;
         for (i64 i = 0; i < n; i++) { u32 v = in[i]; out[i] = (u32)s; s += v; }
-        return s;
+        total[0] = (u32)s;
     }
     void inclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&) {
         u32 s = 0;
@@ -60,6 +79,7 @@ static i64 run_host(const T* logrho, const u32* sorted_pairs, i64 n, i64 E, bool
     void* ws = malloc(bytes);
     AggArena ar(ws, bytes);
     HostExec x;
+    if (const char* e = getenv("HOSTSIM_ORDER")) x.order = atoi(e);
     i64 G = 0;
     int rc = agg::run<HostExec, T>(x, ar, logrho, sorted_pairs, n, E, quirk, ordering, groups, prom, &G);
     free(ws);

@@ -56,3 +56,28 @@ def test_hostsim_matches_oracle_random_graphs(seed):
         assert (o1 == o2).all()
         assert g1.shape == g2.shape and (g1 == g2).all()
         assert np.allclose(p1, p2, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_hostsim_is_independent_of_thread_order(order, monkeypatch):
+    """The passes that race benignly on the GPU (pointer jumping, hooking, the Link1/Link2 rewiring) must give the same
+    result whichever order their threads run in: the host executor replays every pass descending (1) and in a fixed
+    pseudo-random permutation (2) -- two more valid interleavings -- and must still match the oracle."""
+    monkeypatch.setenv("HOSTSIM_ORDER", str(order))
+    rng = np.random.default_rng(100 + order)
+    for trial in range(30):
+        n = int(rng.integers(12, 1200))
+        L = int(rng.integers(2, 9))
+        dtype = np.float32 if trial % 2 else np.float64
+        if trial % 2 == 0:
+            lr = (rng.integers(0, max(2, n // 10), n) / max(1, n // 10)).astype(dtype)
+        else:
+            lr = rng.random(n).astype(dtype)
+        knn = _rand_graph(rng, n, L, trial % 3 != 1)
+        pairs, edges = oracle.make_graph(lr, knn)
+        op = pairs[oracle.sort_edges(edges)]
+        o1, g1, p1 = oracle.aggregate(lr, op)
+        o2, g2, p2 = hostsim.aggregate(lr, op)
+        assert (o1 == o2).all()
+        assert g1.shape == g2.shape and (g1 == g2).all()
+        assert np.allclose(p1, p2, rtol=0, atol=1e-6)
