@@ -9,7 +9,7 @@
 // Device memory layout of the opaque `index` buffer:
 //   [IndexHeader, 256 B]
 //   [perm: u32[NP]]                     index position -> original point (0xffffffff = padding)
-//   [tiles: NLf x tile_stride bytes]    per leaf: lo[d] hi[d] (T) | 16 pair blocks of PB T | ids u32[32]
+//   [tiles: NLf x tile_stride bytes]    per leaf: 16 pair blocks of PB T | ids u32[32]
 //   [boxes level 0..G: count_h rows of box_stride T: lo_0 hi_0 lo_1 hi_1 ... (one row = one node, 16-byte aligned,
 //    so the lane that tests child c reads its whole box with 128-bit loads and (lo_j, hi_j) is one packed f32x2 operand)]
 #pragma once
@@ -32,7 +32,7 @@ struct IndexHeader {
     size_t tiles_off;
     size_t total_bytes;
     int tile_stride;       // bytes, multiple of 128
-    int tile_hdr_bytes;    // lo/hi block, multiple of 16
+    int tile_hdr_bytes;    // bytes before the pair blocks (0)
     int tile_ids_off;      // byte offset of ids within a tile
     int pair_block;        // PB: elements of T per pair block (>= 2d)
     int box_stride;        // BS: elements of T per box row (>= 2d, a multiple of 16 bytes)
@@ -57,7 +57,7 @@ static inline void index_layout(int dtype, i64 n, int d, IndexHeader* h) {
     int eb = elem_bytes(dtype);
     h->pair_block = pair_block_elems(dtype, d);
     h->box_stride = pair_block_elems(dtype, d);
-    h->tile_hdr_bytes = (int)al_align((size_t)2 * d * eb, 16);
+    h->tile_hdr_bytes = 0;      // (a leaf's own box lives in the level-0 box rows; the tile is coordinates + ids only)
     h->tile_ids_off = h->tile_hdr_bytes + (LEAF / 2) * h->pair_block * eb;
     h->tile_stride = (int)al_align((size_t)h->tile_ids_off + LEAF * 4, 128);
     h->count[0] = h->n_leaves;

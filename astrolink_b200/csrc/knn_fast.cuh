@@ -6,74 +6,79 @@
 //
 // Same algorithm, same arithmetic, same results as the generic kernel -- one warp
 // per 32-query leaf, 32-ary box hierarchy with per-child need masks, TMA tile
-// copies double-buffered per warp, per-lane queues merged into per-lane max-heaps
-// in shared memory -- rebuilt around the instruction counts of the round-1 ncu
-// capture (profiles/r02_knn_instruction_budget.md):
-//   * every shared-memory access goes through a 32-bit shared address computed once
-//     (no generic-address arithmetic, no re-derived window base in the loops);
+// copies, per-lane queues merged into per-lane max-heaps in shared memory --
+// rebuilt around the instruction and stall counts of the ncu captures of this
+// round (profiles/r02_knn_*):
+//   * every shared-memory access goes through a 32-bit shared address computed once;
 //     tile geometry is a compile-time function of D;
 //   * sparse tiles: a half-warp holds the whole tile, two candidates per lane as
 //     packed f32x2 operands straight from the pair-interleaved tile, so one pass
 //     evaluates two needy queries (one per half-warp) with D FADD2 + D FFMA2;
 //   * box tests: the index stores a node's box as interleaved (lo_j, hi_j) pairs, one
-//     128-bit-aligned row per node: a lane reads its child's box with 128-bit loads
-//     and a per-axis gap is one FADD2 (q - lo, q - hi), one 3-input max, one FFMA;
+//     128-bit-aligned row per node: a lane reads its child's box with 128-bit loads,
+//     a per-axis gap is one FADD2 (q - lo, q - hi), one 3-input max, one FFMA, and two
+//     needy queries are tested per iteration (two independent chains);
 //   * leaves of a wide node are visited nearest box first with one warp reduction
-//     per tile over a per-lane key register (no mask bookkeeping);
+//     per tile over a per-lane key register;
 //   * heap siblings are adjacent in shared memory, so a sift-down level is one
-//     128-bit load, two 64-bit compares and one store;
-//   * the query leaf's own box lives in shared memory instead of 2 D registers.
+//     128-bit load, two 64-bit compares and one store; the root lives in a register;
+//   * the kernel is latency bound at the occupancy its shared memory allows, so the
+//     per-warp footprint is cut to fit 6 CTAs (24 warps) per SM at d = 6, k = 20:
+//     ONE tile buffer (24 resident warps hide the copy of the next tile better than
+//     a second buffer at 20 warps did), need masks of the list being walked in
+//     registers (lane = child; spilled only on a descent), tiles without a header,
+//     a 7-entry queue.
 #pragma once
+#include <stdlib.h>
+
 #include "knn_kernel.cuh"
 
-#ifndef KF_MINBLOCKS
-#define KF_MINBLOCKS 5
-#endif
 #ifndef KF_SPARSE_MAX
 #define KF_SPARSE_MAX 12       // tiles needed by at most this many queries take the sparse path
 #endif
 #ifndef KF_QCAP
-#define KF_QCAP 8
+#define KF_QCAP 7
 #endif
 #ifndef KF_OPEN2
 #define KF_OPEN2 1             // box tests: two needy queries per iteration (two independent chains)
 #endif
-#ifndef KF_SPARSE4
-#define KF_SPARSE4 1           // sparse tiles: two passes (four needy queries) in flight per iteration
+#ifndef KF_MINBLOCKS
+#define KF_MINBLOCKS 6         // CTAs per SM the register allocation is held to for d <= 8 (80 registers)
 #endif
 
 namespace kf {
 
 constexpr int QC = KF_QCAP;
-static_assert(QC >= 8, "the queue must absorb two dense chunks of four candidates");
+static_assert(QC >= 5, "the queue must hold a dense chunk of four candidates on top of one pending entry");
 
 template <int D>
 struct Geo {
     static constexpr int PB = (2 * D + 3) / 4 * 4;                  // floats per pair block (two candidates, interleaved)
     static constexpr int PB4 = PB / 4;                              // 128-bit words per pair block
-    static constexpr int HDR = (2 * D * 4 + 15) / 16 * 16;          // bytes of the lo/hi header of a tile
-    static constexpr int IDS = HDR + (LEAF / 2) * PB * 4;           // byte offset of the ids inside a tile
+    static constexpr int IDS = (LEAF / 2) * PB * 4;                 // byte offset of the ids inside a tile
     static constexpr int TS = (IDS + LEAF * 4 + 127) / 128 * 128;   // tile stride (bytes)
     static constexpr int RS = (D + 1 + 3) / 4 * 4;                  // floats per query-table row (coordinates, k-th distance)
     static constexpr int RS4 = RS / 4;
     static constexpr int BS = PB;                                   // floats per box row of the index
+    static constexpr int MINB = D <= 8 ? KF_MINBLOCKS : (D <= 12 ? 4 : 3);
 };
 
 // per-warp shared memory (bytes from the warp's base):
-//   tiles[2] | queue [QC][32] u64 | heap root [32] u64 | heap pairs [K/2][32][2] u64 | query table [33][RS] f32 (row 32: a
-//   dummy query nothing is near to) | own leaf box [D] (lo, hi) | need masks [n_levels + 1][32] u32 | stack 3 x [8] | 2 mbarriers
+//   tile | queue [QC][32] u64 | heap pairs [K/2][32][2] u64 (node h's children in pair h; the root in a register) |
+//   query table [32][RS] f32 | own leaf box [D] (lo, hi) | spilled need masks [n_levels - 1][32] u32 | stack masks [8] | mbarrier
+__host__ __device__ static inline int spill_rows(int n_levels) { return n_levels > 1 ? n_levels - 1 : 1; }
 template <int D>
 static inline int warp_smem_bytes(int k, int n_levels) {
     typedef Geo<D> G;
-    size_t b = 2 * (size_t)G::TS;
+    size_t b = (size_t)G::TS;
     b += (size_t)QC * 256;
-    b += 256 + (size_t)(k / 2) * 512;
-    b += (size_t)33 * G::RS * 4;
+    b += (size_t)(k / 2) * 512;
+    b += (size_t)32 * G::RS * 4;
     b += (size_t)G::BS * 4;
-    b += (size_t)(n_levels + 1) * 128;
-    b += 3 * MAX_WIDE_LEVELS * 4;
+    b += (size_t)spill_rows(n_levels) * 128;
+    b += MAX_WIDE_LEVELS * 4;
     b += 16;
-    return (int)al_align(b, 16);      // 16 bytes: what the bulk copies and the 128-bit loads need (d=6, k=20: 11 328 B, 5 CTAs/SM)
+    return (int)al_align(b, 16);      // d=6, k=20, 4 levels: 9 312 B -> 6 CTAs of 4 warps per SM
 }
 
 #ifdef __CUDACC__
@@ -128,7 +133,7 @@ __device__ __forceinline__ u64 make_key(float d, u32 id) { return ((u64)__float_
 __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((u32)(k >> 32)); }
 __device__ __forceinline__ u32 key_id(u64 k) { return (u32)k; }
 
-// row `q` of the query table (uniform or per-half-warp address: a broadcast load)
+// a row of the query table (uniform or per-half-warp address: a broadcast load)
 template <int D>
 __device__ __forceinline__ void load_qrow(u32 row_sa, float* r) {
 #pragma unroll
@@ -138,8 +143,39 @@ __device__ __forceinline__ void load_qrow(u32 row_sa, float* r) {
     }
 }
 
+// Replaces the root of a max-heap of `size` nodes by v and restores the heap.  Node 0 is `root` (a register); node h's
+// children 2h + 1 and 2h + 2 are the two halves of pair h, 512 bytes apart per h from pair0_sa.  A right child that does not
+// exist holds key 0 (never "worse"), except in a heap that is being shrunk (SHRUNK: the epilogue's heapsort), where the slot
+// past the end holds an extracted key and is masked here.
+template <bool SHRUNK>
+__device__ __forceinline__ void heap_replace(u64& root, u32 pair0_sa, int size, u64 v) {
+    const u32 pa_end = pair0_sa + (u32)(size >> 1) * 512u;      // pairs with a left child below `size`
+    if (pair0_sa >= pa_end) { root = v; return; }
+    u64 c0, c1;
+    lds64x2(pair0_sa, c0, c1);
+    if (SHRUNK && pair0_sa + 512u == pa_end && !(size & 1)) c1 = 0ull;
+    u32 r8 = c1 > c0 ? 8u : 0u;
+    u64 ck = r8 ? c1 : c0;
+    if (!(ck > v)) { root = v; return; }
+    root = ck;
+    u32 hole = pair0_sa + r8;
+    u32 pa = pair0_sa + 512u + (r8 << 6);       // node h's worse child is node 2h + 1 + r: offset -> 2 offset + 512 (1 + r)
+#pragma unroll 1
+    while (pa < pa_end) {
+        lds64x2(pa, c0, c1);
+        if (SHRUNK && pa + 512u == pa_end && !(size & 1)) c1 = 0ull;
+        r8 = c1 > c0 ? 8u : 0u;
+        ck = r8 ? c1 : c0;
+        if (!(ck > v)) break;
+        sts64(hole, ck);
+        hole = pa + r8;
+        pa = pair0_sa + 2u * (pa - pair0_sa) + 512u + (r8 << 6);
+    }
+    sts64(hole, v);
+}
+
 template <int D>
-__global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(const KnnParams p) {
+__global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(const KnnParams p) {
     typedef Geo<D> G;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -153,28 +189,21 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
     const int n_levels = p.n_levels;
 
     // ---- shared addresses
-    const u32 tile_sa = smem_u32(smem) + (u32)wib * (u32)p.warp_smem;      // tile buffer 0
-    const u32 queue_sa = tile_sa + 2u * G::TS + (u32)lane * 8u;            // this lane's queue slot 0 (slot stride 256)
-    const u32 root_sa = tile_sa + 2u * G::TS + QC * 256u + (u32)lane * 8u; // this lane's heap root
-    const u32 pair_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)lane * 16u;     // this lane's pair 0 (pair stride 512)
-    // query table: row -1 is a dummy query nothing is near to (the partner of the last query of an odd sparse pass)
-    const u32 qt_sa = tile_sa + 2u * G::TS + QC * 256u + 256u + (u32)NP * 512u + G::RS * 4u;
+    const u32 tile_sa = smem_u32(smem) + (u32)wib * (u32)p.warp_smem;      // the tile buffer
+    const u32 queue_sa = tile_sa + G::TS + (u32)lane * 8u;                 // this lane's queue slot 0 (slot stride 256)
+    const u32 pair_sa = tile_sa + G::TS + QC * 256u + (u32)lane * 16u;     // this lane's pair 0 (pair stride 512)
+    const u32 qt_sa = tile_sa + G::TS + QC * 256u + (u32)NP * 512u;        // query table
     const u32 qbox_sa = qt_sa + 32u * G::RS * 4u;                          // own leaf's box, (lo_j, hi_j) pairs
-    const u32 need_sa = qbox_sa + G::BS * 4u;                              // [n_levels + 1][32] need masks
-    const u32 stk_sa = need_sa + (u32)(n_levels + 1) * 128u;               // stack: mask[8] | node[8] | level[8]
-    const u32 bar_sa = stk_sa + 3u * MAX_WIDE_LEVELS * 4u;                 // 2 mbarriers
+    const u32 need_sa = qbox_sa + G::BS * 4u + (u32)lane * 4u;             // spilled need masks, this lane's column (row stride 128)
+    const u32 stk_sa = qbox_sa + G::BS * 4u + (u32)spill_rows(n_levels) * 128u;    // children masks of the entries below the top
+    const u32 bar_sa = stk_sa + MAX_WIDE_LEVELS * 4u;                      // the tile buffer's mbarrier
     const u32 myrow_sa = qt_sa + (u32)lane * (G::RS * 4u);
 
     const u64 kinf = make_key(INFINITY, 0xffffffffu);
     if (lane == 0) {
         mbar_init_sa(bar_sa, 1);
-        mbar_init_sa(bar_sa + 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the dummy query of an odd sparse pass: nothing is within distance -1 of it
-#pragma unroll
-        for (int j = 0; j < G::RS; j++) stsf(qt_sa - G::RS * 4u + 4u * j, j == D ? -1.f : 0.f);
     }
-    sts64(root_sa, kinf);
 #pragma unroll 1
     for (int h = 0; h < NP; h++) sts64x2(pair_sa + (u32)h * 512u, kinf, (2 * h + 2 < K) ? kinf : 0ull);   // a missing right sibling is never "worse"
 #pragma unroll
@@ -185,31 +214,11 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
     float q[D];
     float worst = -1.f;         // k-th distance so far (-1: padding lane)
     float bound = INFINITY;     // warp max of worst
-    u64 root = kinf;            // cached heap root
+    u64 root = kinf;            // heap node 0
     int cnt = 0;                // queue fill
     u32 my_id = 0xffffffffu;
     u32 n_qt = 0;               // (query, tile) evaluations
     u32 st_loaded = 0, st_dense = 0, st_push = 0, st_insert = 0, st_rounds = 0, st_open_iter = 0, st_descents = 0;
-
-    // replace the heap root by v (v is better than the root) and restore the heap
-    auto sift = [&](u64 v) {
-        u32 hole = root_sa;
-        u32 pa = pair_sa;                   // pair h (the children of node h) of this lane
-        const u32 pa_end = pair_sa + (u32)NP * 512u;
-#pragma unroll 1
-        while (pa < pa_end) {
-            u64 c0, c1;
-            lds64x2(pa, c0, c1);
-            const u32 r8 = c1 > c0 ? 8u : 0u;
-            const u64 ck = r8 ? c1 : c0;
-            if (!(ck > v)) break;
-            sts64(hole, ck);
-            hole = pa + r8;
-            // node h's worse child is node 2h + 1 + r; in bytes from pair 0: off -> 2 off + 512 (1 + r)
-            pa = pair_sa + 2u * (pa - pair_sa) + 512u + (r8 << 6);
-        }
-        sts64(hole, v);
-    };
 
     auto flush = [&]() {
         const int maxc = __reduce_max_sync(FULL, cnt);
@@ -217,8 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         for (int t = 0; t < maxc; t++) {
             const u64 v = lds64(queue_sa + (u32)t * 256u);      // slots past cnt hold stale keys: masked by the test below
             if (t < cnt && root > v) {
-                sift(v);
-                root = lds64(root_sa);
+                heap_replace<false>(root, pair_sa, K, v);
                 if (KNN_STATS) st_insert++;
             }
             if (KNN_STATS) st_rounds++;
@@ -232,9 +240,9 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
 
     // Open a wide node: lane j takes child j (a level-`hc` node), box-to-box test against the warp bound, then for every
     // query in `qmask` the distance from the query to the child's box against the query's own k-th distance.  The child's
-    // need mask goes to shared memory at out_sa; `okey` becomes this lane's visiting-order key (box distance | lane).
-    u32 okey = 0xffffffffu;
-    auto open_node = [&](int hc, int node, int excl, u32 qmask, u32 out_sa) -> u32 {
+    // need mask stays in this lane's `cmask`; `okey` becomes its visiting-order key (box distance | lane).
+    u32 okey = 0xffffffffu, cmask = 0;
+    auto open_node = [&](int hc, int node, int excl, u32 qmask) -> u32 {
         const int count = (int)p.count[hc];
         const int c = node * FANOUT + lane;
         const bool ok = c < count && c != excl;
@@ -277,15 +285,14 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
 #if KF_OPEN2
 #pragma unroll 1
             while (m) {
-                // two needy queries per iteration (independent chains); an odd count pairs the last one with the dummy
-                // query (row -1, k-th distance -1: never needed)
+                // two needy queries per iteration (independent chains); an odd count tests the last one twice
                 const u32 ba = m & (0u - m);
                 m ^= ba;
                 const u32 bb = m & (0u - m);
                 m ^= bb;
                 float ka, kb;
                 const float pa = box_dist(31 - __clz(ba), ka);
-                const float pb = box_dist(31 - __clz(bb), kb);
+                const float pb = box_dist(31 - __clz(bb ? bb : ba), kb);
                 if (pa <= ka) mask |= ba;
                 if (pb <= kb) mask |= bb;
                 if (KNN_STATS) st_open_iter++;
@@ -303,12 +310,14 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
 #endif
             mask = pass ? mask : 0u;
         }
-        sts32(out_sa + 4u * lane, mask);
+        cmask = mask;
         okey = mask != 0 ? ((__float_as_uint(acc) & ~31u) | (u32)lane) : 0xffffffffu;      // order only: 27 bits of distance are plenty
         return __ballot_sync(FULL, mask != 0);
     };
 
-    // ---- traversal state: ancestors of the own leaf bottom-up; a small stack for descents (top entry in registers)
+    // ---- traversal state: ancestors of the own leaf bottom-up; a small stack for descents.  The top entry (children still to
+    // visit, node, level; per-child need masks in cmask, lane = child) lives in registers.  Entries below it keep their
+    // children mask and need masks in shared memory; their node and level follow from the child's (node >> 5, level + 1).
     int anc = 1, sp = 0;
     u32 t_mask = 0;
     int t_node = 0, t_h = 0;
@@ -319,10 +328,9 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 if (anc > n_levels) return -1;
                 if (__any_sync(FULL, cnt > 0)) flush();
                 const int node = ql >> (5 * anc), excl = ql >> (5 * (anc - 1));
-                t_mask = open_node(anc - 1, node, excl, FULL, need_sa);
+                t_mask = open_node(anc - 1, node, excl, FULL);
                 t_node = node;
                 t_h = anc;
-                __syncwarp();
                 sp = 1;
                 anc++;
                 continue;
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 if (kmin != 0xffffffffu) {
                     const u32 bit = kmin & 31u;
                     if ((u32)lane == bit) okey = 0xffffffffu;
-                    cand_need = lds32(need_sa + ((u32)(sp - 1) * 32u + bit) * 4u);
+                    cand_need = __shfl_sync(FULL, cmask, (int)bit);
                     return t_node * FANOUT + (int)bit;
                 }
                 t_mask = 0;
@@ -343,23 +351,21 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 sp--;
                 if (sp > 0) {
                     t_mask = lds32(stk_sa + (u32)(sp - 1) * 4u);
-                    t_node = (int)lds32(stk_sa + (u32)(MAX_WIDE_LEVELS + sp - 1) * 4u);
-                    t_h = (int)lds32(stk_sa + (u32)(2 * MAX_WIDE_LEVELS + sp - 1) * 4u);
+                    cmask = lds32(need_sa + (u32)(sp - 1) * 128u);
+                    t_node >>= 5;
+                    t_h++;
                 }
                 continue;
             }
             const int bit = __ffs(t_mask) - 1;
             t_mask &= t_mask - 1;
-            const u32 need = lds32(need_sa + ((u32)(sp - 1) * 32u + (u32)bit) * 4u);
+            const u32 need = __shfl_sync(FULL, cmask, bit);
             const int c = t_node * FANOUT + bit;
-            // descend: save the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
-            if (lane == 0) {
-                sts32(stk_sa + (u32)(sp - 1) * 4u, t_mask);
-                sts32(stk_sa + (u32)(MAX_WIDE_LEVELS + sp - 1) * 4u, (u32)t_node);
-                sts32(stk_sa + (u32)(2 * MAX_WIDE_LEVELS + sp - 1) * 4u, (u32)t_h);
-            }
+            // descend: spill the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
+            sts32(need_sa + (u32)(sp - 1) * 128u, cmask);
+            if (lane == 0) sts32(stk_sa + (u32)(sp - 1) * 4u, t_mask);
             if (KNN_STATS) st_descents++;
-            t_mask = open_node(t_h - 2, c, -1, need, need_sa + (u32)sp * 128u);
+            t_mask = open_node(t_h - 2, c, -1, need);
             t_node = c;
             t_h = t_h - 1;
             __syncwarp();
@@ -367,19 +373,19 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         }
     };
 
-    // Tile t of this warp lands in buffer t & 1 and completes phase (t >> 1) & 1 of that buffer's barrier.
-    auto issue_tile = [&](int leaf, u32 buf) {
+    // Tile number t of this warp completes phase t & 1 of the buffer's barrier.
+    auto issue_tile = [&](int leaf) {
         if (lane == 0) {
-            mbar_expect_tx_sa(bar_sa + 8u * buf, (u32)G::TS);
-            tma_load_1d_sa(tile_sa + buf * (u32)G::TS, p.tiles + (size_t)(u32)leaf * (u32)G::TS, (u32)G::TS, bar_sa + 8u * buf);
+            mbar_expect_tx_sa(bar_sa, (u32)G::TS);
+            tma_load_1d_sa(tile_sa, p.tiles + (size_t)(u32)leaf * (u32)G::TS, (u32)G::TS, bar_sa);
         }
         if (KNN_STATS) st_loaded++;
     };
     auto wait_tile = [&](u32 t) {
-        while (!mbar_try_wait_sa(bar_sa + 8u * (t & 1u), (t >> 1) & 1u)) {}
+        while (!mbar_try_wait_sa(bar_sa, t & 1u)) {}
     };
 
-    // one hit of a sparse pass: owner lane `qi` queues the candidate held by lane `src`
+    // hits of one query of a sparse pass: owner lane `qi` queues every candidate flagged in `hm` (held by lane bit + laneoff)
     auto emit = [&](u32 hm, float val, u32 id, int qi, int laneoff) {
 #pragma unroll 1
         while (hm) {
@@ -396,11 +402,9 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         }
     };
 
-    // ---- dense: every lane evaluates all 32 candidates of the tile in buffer `bw`, two per instruction (packed f32x2,
-    // broadcast tile reads)
-    auto eval_dense = [&](u32 bw) {
-        const u32 coords_sa = tile_sa + bw * (u32)G::TS + (u32)G::HDR;
-        const u32 ids_sa = tile_sa + bw * (u32)G::TS + (u32)G::IDS;
+    // ---- dense: every lane evaluates all 32 candidates of the tile, two per instruction (packed f32x2, broadcast tile reads)
+    auto eval_dense = [&]() {
+        const u32 ids_sa = tile_sa + (u32)G::IDS;
         if (KNN_STATS) st_dense++;
         n_qt += 32;
         if (__any_sync(FULL, cnt > QC - 4)) flush();        // the sparse path can leave queues fuller than a chunk allows
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 u64 acc = 0ull;
 #pragma unroll
                 for (int v4 = 0; v4 < G::PB4; v4++) {
-                    const float4 f = lds_f4(coords_sa + (u32)((pb0 + c) * G::PB4 + v4) * 16u);
+                    const float4 f = lds_f4(tile_sa + (u32)((pb0 + c) * G::PB4 + v4) * 16u);
                     if (2 * v4 < D) {
                         const u64 df = sub2(pack2(q[2 * v4], q[2 * v4]), pack2(f.x, f.y));
                         acc = fma2(df, df, acc);
@@ -439,23 +443,20 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         }
     };
 
-    // ---- sparse: each half-warp holds the whole tile (lanes l and l + 16: candidates 2 (l & 15) and 2 (l & 15) + 1 as
-    // packed pairs, exactly the tile's pair block, in `c4`); the lower half evaluates one needy query, the upper half another.
-    // `ids_of` yields this lane's two candidate ids; it is only called when a pass has a hit.
+    // ---- sparse: each half-warp holds the whole tile (lanes l and l + 16: candidates 2 (l & 15) and 2 (l & 15) + 1 as packed
+    // pairs -- exactly the tile's pair block -- in `cand`, their ids in id0/id1); per pass the lower half evaluates one needy
+    // query, the upper half another (an odd count: the same one again, its hits ignored).
     const u32 hl = (u32)lane & 15u;
-    auto eval_sparse = [&](const float4* c4, u32 need, auto ids_of) {
+    auto eval_sparse = [&](const u64* cand, u32 id0, u32 id1, u32 need) {
         n_qt += __popc(need);
-        u64 cand[D + 1];
-#pragma unroll
-        for (int v4 = 0; v4 < G::PB4; v4++) {
-            if (2 * v4 < D) cand[2 * v4] = pack2(c4[v4].x, c4[v4].y);
-            if (2 * v4 + 1 < D) cand[2 * v4 + 1] = pack2(c4[v4].z, c4[v4].w);
-        }
         u32 m = need;
-        // one pass: the lower half-warp evaluates the query of bit `ba`, the upper half the query of bit `bb` (0: the dummy
-        // query, row -1, whose k-th distance is -1) against this lane's two candidates
-        auto pass_dist = [&](u32 ba, u32 bb, float& d0, float& d1, float& kth) {
-            const int myq = 31 - __clz(lane < 16 ? ba : bb);
+#pragma unroll 1
+        while (m) {
+            const u32 ba = m & (0u - m);
+            m ^= ba;
+            const u32 bb = m & (0u - m);
+            m ^= bb;
+            const int myq = 31 - __clz((lane < 16 || bb == 0u) ? ba : bb);
             float row[G::RS];
             load_qrow<D>(qt_sa + (u32)(myq * (G::RS * 4)), row);
             u64 acc = 0ull;
@@ -464,70 +465,26 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 const u64 df = sub2(pack2(row[j], row[j]), cand[j]);
                 acc = fma2(df, df, acc);
             }
+            float d0, d1;
             unpack2(acc, d0, d1);
-            kth = row[D];
-        };
-        auto pass_hits = [&](u32 ba, u32 bb, float d0, float d1, bool h0, bool h1) {
-            const u32 b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
-            if ((b0 | b1) == 0u) return;
-            u32 id0, id1;
-            ids_of(id0, id1);
-            const int qa = 31 - __clz(ba), qb = 31 - __clz(bb);
-            emit(b0 & 0xffffu, d0, id0, qa, 0);
-            emit(b1 & 0xffffu, d1, id1, qa, 0);
-            emit(b0 >> 16, d0, id0, qb, 16);        // no hits when bb == 0
-            emit(b1 >> 16, d1, id1, qb, 16);
-        };
-#if KF_SPARSE4
-#pragma unroll 1
-        while (m) {
-            // two passes (up to four needy queries) per iteration: two independent load + FMA chains in flight
-            const u32 ba = m & (0u - m);
-            m ^= ba;
-            const u32 bb = m & (0u - m);
-            m ^= bb;
-            const u32 bc = m & (0u - m);
-            m ^= bc;
-            const u32 bd = m & (0u - m);
-            m ^= bd;
-            float d0, d1, k0, e0, e1, k1;
-            pass_dist(ba, bb, d0, d1, k0);
-            pass_dist(bc, bd, e0, e1, k1);        // bc == bd == 0: both halves take the dummy query
-            const bool h0 = d0 <= k0, h1 = d1 <= k0, g0 = e0 <= k1, g1 = e1 <= k1;
-            if (__any_sync(FULL, h0 || h1 || g0 || g1)) {       // the common iteration has no hit at all: one vote, one branch
-                pass_hits(ba, bb, d0, d1, h0, h1);
-                pass_hits(bc, bd, e0, e1, g0, g1);
+            const bool h0 = d0 <= row[D], h1 = d1 <= row[D];
+            if (__any_sync(FULL, h0 || h1)) {       // the common pass has no hit at all: one vote, one branch
+                u32 b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
+                if (bb == 0u) { b0 &= 0xffffu; b1 &= 0xffffu; }
+                const int qa = 31 - __clz(ba), qb = 31 - __clz(bb | 1u);
+                emit(b0 & 0xffffu, d0, id0, qa, 0);
+                emit(b1 & 0xffffu, d1, id1, qa, 0);
+                emit(b0 >> 16, d0, id0, qb, 16);
+                emit(b1 >> 16, d1, id1, qb, 16);
             }
         }
-#else
-#pragma unroll 1
-        while (m) {
-            const u32 ba = m & (0u - m);
-            m ^= ba;
-            const u32 bb = m & (0u - m);
-            m ^= bb;
-            float d0, d1, k0;
-            pass_dist(ba, bb, d0, d1, k0);
-            const bool h0 = d0 <= k0, h1 = d1 <= k0;
-            if (__any_sync(FULL, h0 || h1)) pass_hits(ba, bb, d0, d1, h0, h1);
-        }
-#endif
-    };
-    // the same from the tile in shared-memory buffer `bw`
-    auto eval_sparse_smem = [&](u32 bw, u32 need) {
-        const u32 coords_sa = tile_sa + bw * (u32)G::TS + (u32)G::HDR;
-        const u32 ids_sa = tile_sa + bw * (u32)G::TS + (u32)G::IDS;
-        float4 c4[G::PB4];
-#pragma unroll
-        for (int v4 = 0; v4 < G::PB4; v4++) c4[v4] = lds_f4(coords_sa + hl * (G::PB * 4u) + 16u * v4);
-        eval_sparse(c4, need, [&](u32& id0, u32& id1) { lds32x2(ids_sa + hl * 8u, id0, id1); });
     };
 
-    // ---- own leaf (tile 0, no look-ahead: the box tests need the queries and their first bounds)
-    issue_tile(ql, 0u);
+    // ---- own leaf (tile 0)
+    issue_tile(ql);
     wait_tile(0u);
     {
-        const u32 mine = tile_sa + (u32)G::HDR + (u32)(lane >> 1) * (G::PB * 4u) + (u32)(lane & 1) * 4u;
+        const u32 mine = tile_sa + (u32)(lane >> 1) * (G::PB * 4u) + (u32)(lane & 1) * 4u;
 #pragma unroll
         for (int j = 0; j < D; j++) {
             q[j] = ldsf(mine + 8u * j);
@@ -537,56 +494,57 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
         worst = my_id != 0xffffffffu ? INFINITY : -1.f;
         stsf(myrow_sa + 4u * D, worst);
         __syncwarp();
-        eval_dense(0u);
+        eval_dense();
     }
-    // ---- the other leaves: while tile t is evaluated, the traversal has already found tile t + 1 and its copy is in flight
-    int cur = next_candidate();
-    if (cur >= 0) {
+    // ---- the other leaves.  One buffer: the traversal finds tile t + 1 while the copy of tile t is in flight, and the copy of
+    // tile t + 1 is issued when tile t has been evaluated.  (Issuing it as soon as a sparse tile has been moved to registers,
+    // under its passes, was measured slower -- 74.0 against 71.8 ms on C4 -- and needs the copy ordered after the RETURN of
+    // those loads, not their issue: with 128-byte pair blocks, d >= 15, their bank conflicts outlast a copy served from L2.)
+    const int first = next_candidate();
+    if (first >= 0) {
         u32 cur_need = cand_need;
         u32 t = 1;
-        issue_tile(cur, 1u);
+        __syncwarp();       // every lane is done reading the own leaf
+        issue_tile(first);
 #pragma unroll 1
         for (;;) {
             const int nxt = next_candidate();
             const u32 nxt_need = cand_need;
-            if (nxt >= 0) {
-                __syncwarp();       // every lane is done reading the other buffer
-                issue_tile(nxt, (t & 1u) ^ 1u);
-            }
             wait_tile(t);
-            if (KNN_BRUTE || __popc(cur_need) > KF_SPARSE_MAX) eval_dense(t & 1u);
-            else eval_sparse_smem(t & 1u, cur_need);
+            if (KNN_BRUTE || __popc(cur_need) > KF_SPARSE_MAX) {
+                eval_dense();
+            } else {
+                u64 cand[D + 1];
+#pragma unroll
+                for (int v4 = 0; v4 < G::PB4; v4++) {
+                    const float4 f = lds_f4(tile_sa + hl * (G::PB * 4u) + 16u * v4);
+                    if (2 * v4 < D) cand[2 * v4] = pack2(f.x, f.y);
+                    if (2 * v4 + 1 < D) cand[2 * v4 + 1] = pack2(f.z, f.w);
+                }
+                u32 id0, id1;
+                lds32x2(tile_sa + (u32)G::IDS + hl * 8u, id0, id1);
+                eval_sparse(cand, id0, id1, cur_need);
+            }
             if (nxt < 0) break;
+            __syncwarp();       // every lane is done with the tile (its loads have been consumed)
+            issue_tile(nxt);
             cur_need = nxt_need;
             t++;
         }
     }
     if (__any_sync(FULL, cnt > 0)) flush();
 
-    // ---- heap -> ascending order in place (heapsort over the paired layout), then the outputs
+    // ---- heap -> ascending order in place (heapsort over the paired layout; node 0 ends up in queue slot 0), then the outputs
     auto node_sa = [&](int m, int r) -> u32 {       // heap node m of lane r
-        return m == 0 ? root_sa + (u32)(r - lane) * 8u : pair_sa + (u32)(r - lane) * 16u + (u32)((m - 1) >> 1) * 512u + (u32)((m - 1) & 1) * 8u;
+        return m == 0 ? queue_sa + (u32)(r - lane) * 8u : pair_sa + (u32)(r - lane) * 16u + (u32)((m - 1) >> 1) * 512u + (u32)((m - 1) & 1) * 8u;
     };
 #pragma unroll 1
     for (int m = K - 1; m >= 1; m--) {
         const u64 v = lds64(node_sa(m, lane));
-        sts64(node_sa(m, lane), lds64(root_sa));
-        // sift v down from the root of a heap of m nodes
-        u32 hole = root_sa;
-        int h = 0;
-#pragma unroll 1
-        while (2 * h + 1 < m) {
-            u64 c0, c1;
-            lds64x2(pair_sa + (u32)h * 512u, c0, c1);
-            const bool r = (2 * h + 2 < m) && c1 > c0;
-            const u64 ck = r ? c1 : c0;
-            if (!(ck > v)) break;
-            sts64(hole, ck);
-            hole = pair_sa + (u32)h * 512u + (r ? 8u : 0u);
-            h = 2 * h + 1 + (r ? 1 : 0);
-        }
-        sts64(hole, v);
+        sts64(node_sa(m, lane), root);      // the largest of the m + 1 remaining keys
+        heap_replace<true>(root, pair_sa, m, v);
     }
+    sts64(queue_sa, root);
     const bool active = my_id != 0xffffffffu;
     const i64 pos_row = ((i64)blockIdx.x * WARPS + wib) * LEAF + lane;      // row of this launch (row_order 1)
     if (active) {
@@ -642,7 +600,7 @@ __global__ void __launch_bounds__(WARPS * 32, KF_MINBLOCKS) knn_fast_kernel(cons
                 atomicAdd(p.stats + 2, (unsigned long long)st_dense);           // of which evaluated densely
                 atomicAdd(p.stats + 3, (unsigned long long)st_descents);        // wide nodes opened below the ancestors
                 atomicAdd(p.stats + 6, (unsigned long long)st_rounds);          // flush rounds
-                atomicAdd(p.stats + 7, (unsigned long long)st_open_iter);       // per-query iterations of the box tests
+                atomicAdd(p.stats + 7, (unsigned long long)st_open_iter);       // iterations of the box-test loop
             }
         }
         if (KNN_STATS) {
@@ -659,7 +617,7 @@ template <int D>
 static int launch(const KnnParams& p0, cudaStream_t st) {
     typedef Geo<D> G;
     KnnParams p = p0;
-    AL_REQUIRE(p.tile_stride == G::TS && p.tile_hdr_bytes == G::HDR && p.tile_ids_off == G::IDS && p.pair_block == G::PB &&
+    AL_REQUIRE(p.tile_stride == G::TS && p.tile_hdr_bytes == 0 && p.tile_ids_off == G::IDS && p.pair_block == G::PB &&
                p.box_stride == G::BS, AL_EINTERNAL, "al_knn: index geometry does not match the float kernel's (d=%d)", D);
     i64 n_q = p.leaf_end - p.leaf_begin;
     if (p.chunk_blocks > 0) {
@@ -672,6 +630,14 @@ static int launch(const KnnParams& p0, cudaStream_t st) {
     const size_t smem = (size_t)p.warp_smem * WARPS;
     AL_REQUIRE(smem <= 227 * 1024, AL_EINVAL, "al_knn: k too large for shared memory");
     if (smem > 48 * 1024) AL_CUDA(cudaFuncSetAttribute(knn_fast_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // all of the SM's shared memory for CTAs: occupancy is set by the per-warp footprint above
+    AL_CUDA(cudaFuncSetAttribute(knn_fast_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    if (getenv("AL_KNN_DEBUG") != nullptr) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, knn_fast_kernel<D>, WARPS * 32, smem);
+        fprintf(stderr, "[al_knn] d=%d k=%d levels=%d: %zu B shared memory per CTA, %d CTAs (%d warps) per SM\n", D, p.k, p.n_levels, smem, nb,
+                nb * WARPS);
+    }
     knn_fast_kernel<D><<<(unsigned)((n_q + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(p);
     AL_CHECK_LAUNCH();
     return AL_OK;

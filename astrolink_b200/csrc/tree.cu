@@ -230,7 +230,10 @@ constexpr int BOT_LEAVES = 128;
 constexpr int BOT_POINTS = BOT_LEAVES * LEAF;     // 4096
 constexpr int BOT_THREADS = 512;
 constexpr int BOT_ITEMS = BOT_POINTS / BOT_THREADS;
-typedef cub::BlockRadixSort<u32, BOT_THREADS, BOT_ITEMS, u32> BotSort;
+#ifndef AL_BOT_RADIX_BITS
+#define AL_BOT_RADIX_BITS 4
+#endif
+typedef cub::BlockRadixSort<u32, BOT_THREADS, BOT_ITEMS, u32, AL_BOT_RADIX_BITS> BotSort;
 
 static size_t tree_bottom_smem(int d) {
     return (size_t)BOT_POINTS * d * 4 + (size_t)BOT_POINTS * 4 * 2 + (size_t)BOT_LEAVES * (2 + 2 * d + 4) * 4 + sizeof(BotSort::TempStorage) + 64;
@@ -383,7 +386,6 @@ __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restri
     u32 id = valid ? perm[p] : 0xffffffffu;
     if (!valid) perm[p] = 0xffffffffu;
     char* tile = tiles + leaf * (i64)h.tile_stride;
-    T* hdr = (T*)tile;
     T* coords = (T*)(tile + h.tile_hdr_bytes);
     u32* ids = (u32*)(tile + h.tile_ids_off);
     ids[lane] = id;
@@ -400,8 +402,6 @@ __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restri
             b = b2 > b ? b2 : b;
         }
         if (lane == 0) {
-            hdr[j] = a;
-            hdr[d + j] = b;
             box0[leaf * h.box_stride + 2 * j] = a;
             box0[leaf * h.box_stride + 2 * j + 1] = b;
         }

@@ -189,3 +189,41 @@ def test_object_pickles_like_the_reference(tmp_path):
     np.savez(tmp_path / "obj.npz", clusterer=c)
     c3 = np.load(tmp_path / "obj.npz", allow_pickle=True)["clusterer"].item()
     assert np.array_equal(c3.ordering, c.ordering)
+
+
+def test_io_round_trip_and_plotting_surface(tmp_path, golden):
+    """f4: astrolink_b200.io mirrors the reference's io.saveAstroLinkObject / loadAstroLinkObject
+    (io.py:12-46), and a loaded object exposes every attribute the reference's plotting functions read
+    (visualize.py:57-80, 116-154, 216-225, 291-303, 336, 379-381) with the reference's dtypes and shapes -- taken here
+    from the reference's own outputs for the README example (tests/golden/readme_c1_f64.npz)."""
+    from astrolink_b200 import AstroLink, io
+    g = golden("readme_c1_f64")
+    c = AstroLink(g["P"])
+    c.run()
+    io.saveAstroLinkObject(c, str(tmp_path / "clusterer"))            # numpy appends .npz, as for the reference
+    c2 = io.loadAstroLinkObject(str(tmp_path / "clusterer"))
+    assert not any(k.startswith("_d_") for k in c2.__dict__), "no device tensors in a loaded object"
+    ref = {"logRho": g["logRho"], "ordering": g["ordering"], "groups": g["groups"], "prominences": g["prominences"],
+           "groups_sigs": g["groups_sigs"], "clusters": g["clusters"], "significances": g["significances"], "pFit": g["pFit"]}
+    for name, r in ref.items():
+        a = getattr(c2, name)
+        assert isinstance(a, np.ndarray), name
+        assert a.dtype == r.dtype and a.shape == r.shape, (name, a.dtype, r.dtype, a.shape, r.shape)
+        assert np.array_equal(a, getattr(c, name)), name
+    assert np.asarray(c2.ids).dtype.kind == "U" and list(c2.ids) == list(g["ids"])
+    assert isinstance(c2.S, float) and c2.n_samples == g["P"].shape[0] and c2.k_link == int(g["k_link"])
+    # the plotting functions index ordering / clusters like this (visualize.py:116-154)
+    assert (c2.logRho[c2.ordering][c2.clusters[1, 0]:c2.clusters[1, 1]]).size == c2.clusters[1, 1] - c2.clusters[1, 0]
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        return
+    import importlib.util
+    import os
+    path = "/root/reference/astrolink/visualize.py"
+    if not os.path.exists(path):
+        return
+    spec = importlib.util.spec_from_file_location("ref_visualize", path)
+    vis = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vis)
+    vis.plotOrderedDensity(c2)
