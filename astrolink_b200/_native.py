@@ -47,6 +47,7 @@ _SIGS = {
     "al_peer_alloc": (_int, [_sz, _vp, _vp]),
     "al_peer_open": (_int, [_vp, _vp]),
     "al_peer_release": (_int, [_vp, _int]),
+    "al_peer_copy": (_int, [_vp, _vp, _sz, _vp]),
     "al_knn_link": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
     "al_knn_dealt": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
     "al_knn_dealt_rows": (_i64, [_i64, _i64, _i64, _i64]),
@@ -251,6 +252,16 @@ class PeerArray:
         for s in self.shape[i + 1:]:
             st *= s
         return st
+
+
+def index_positions(n):
+    """Number of index positions of an n-point index (n rounded up to whole leaves)."""
+    return int(lib().al_index_positions(int(n)))
+
+
+def peer_copy(dst, src, nbytes):
+    """Asynchronous device-to-device copy on the current stream; dst / src: tensors or PeerArrays."""
+    _check(lib().al_peer_copy(_ptr(dst), _ptr(src), int(nbytes), _stream()), "al_peer_copy")
 
 
 def enable_peer_access(peer_device):

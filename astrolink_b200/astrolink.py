@@ -220,6 +220,14 @@ class AstroLink:
             return 0, 1
         return d.get_rank(), d.get_world_size()
 
+    def _search_width(self):
+        """This rank's share of the search in dealt chunks per round (peer path; see dist.tail_aware_widths); None when the
+        run is not sharded that way."""
+        d = self._dist
+        if d is None or d.get_world_size() == 1 or getattr(d, "peer", None) is None:
+            return None
+        return d.widths[d.get_rank()]
+
     def _is_result_rank(self):
         return self._world()[0] == 0
 
@@ -228,6 +236,10 @@ class AstroLink:
         """adaptive=1: every feature divided by its standard deviation; adaptive=0:
         untouched (astrolink.py:218-234).  Creates `P_transform`."""
         start = time.perf_counter()
+        if self._search_width() == 0:
+            # multi-GPU, dedicated tail rank: it neither searches nor builds an index, so P never goes to its GPU
+            self._transformTime = time.perf_counter() - start
+            return
         with torch.cuda.device(self._device):
             dP = self.__dict__.get("_d_P_in")
             if dP is None:
@@ -253,41 +265,44 @@ class AstroLink:
             self._printFunction('Computing densities...    ')
         start = time.perf_counter()
         with torch.cuda.device(self._device):
-            Pt = self._dev("P_transform")
-            if not Pt.is_contiguous():
-                Pt = Pt.contiguous()
             n, K, L = self.n_samples, self.k_den, self.k_link
-            a, b = self._stage("index_build")
-            a.record()
-            index = nat.Index(Pt)
-            b.record()
-            self._index_positions = index.positions
             w = None
             if self.weights is not None:
                 w = self._to_device(np.asarray(self.weights, dtype=np.float64))
             rank, world = self._world()
-            if world == 1:
-                a, b = self._stage("knn")
-                a.record()
-                # the k_link nearest ids go straight to their own [n, k_link] array (astrolink.py:286) from the
-                # search kernel's epilogue; the full index rows are only written when the weights need them
-                kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
-                if w is None:
-                    # a4 fused into the search epilogue (al_knn_density): the [n, k_den] distance array is never written
-                    raw = torch.empty((n,), dtype=Pt.dtype, device=self._device)
-                    _, _, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=False,
-                                                      logrho_out=raw, d_intrinsic=self.d_intrinsic, want_d2=False)
-                    b.record()
-                else:
-                    d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=True)
-                    b.record()
-                    a, b = self._stage("density")
-                    a.record()
-                    raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
-                    b.record()
-                    del d2, idx
+            if self._search_width() is not None:
+                raw, kNN = self._sharded_knn_peer(w, rank)
             else:
-                raw, kNN = self._sharded_knn(index, w, rank, world)
+                Pt = self._dev("P_transform")
+                if not Pt.is_contiguous():
+                    Pt = Pt.contiguous()
+                a, b = self._stage("index_build")
+                a.record()
+                index = nat.Index(Pt)
+                b.record()
+                self._index_positions = index.positions
+                if world == 1:
+                    a, b = self._stage("knn")
+                    a.record()
+                    # the k_link nearest ids go straight to their own [n, k_link] array (astrolink.py:286) from the
+                    # search kernel's epilogue; the full index rows are only written when the weights need them
+                    kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
+                    if w is None:
+                        # a4 fused into the search epilogue (al_knn_density): the [n, k_den] distance array is never written
+                        raw = torch.empty((n,), dtype=Pt.dtype, device=self._device)
+                        _, _, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=False,
+                                                          logrho_out=raw, d_intrinsic=self.d_intrinsic, want_d2=False)
+                        b.record()
+                    else:
+                        d2, idx, self._knn_pairs = index.knn(K, row_order=0, count_pairs=True, link_out=kNN, want_idx=True)
+                        b.record()
+                        a, b = self._stage("density")
+                        a.record()
+                        raw = nat.logrho(d2, idx, K, self.d_intrinsic, weights=w)
+                        b.record()
+                        del d2, idx
+                else:
+                    raw, kNN = self._sharded_knn(index, w, rank, world)
             # with the peer exchange only rank 0 holds the densities (results live on rank 0)
             a, b = self._stage("normalise")
             a.record()
@@ -295,7 +310,8 @@ class AstroLink:
             b.record()
             self._set_dev("logRho", lr)
             self._set_dev("kNN", kNN)
-            del self.P_transform
+            if "_d_P_transform" in self.__dict__ or "_h_P_transform" in self.__dict__:
+                del self.P_transform
         self._logRhoTime = time.perf_counter() - start
 
     def _sharded_knn(self, index, w, rank, world):
@@ -305,9 +321,6 @@ class AstroLink:
         from . import dist as adist
         n, K, L = self.n_samples, self.k_den, self.k_link
         lo, hi, per = adist.shard_positions(index.positions, rank, world, nat.LEAF)
-        peer = getattr(self._dist, "peer", None)
-        if peer is not None:
-            return self._sharded_knn_peer(index, w, rank, lo, hi, peer)
         a, b = self._stage("knn")
         a.record()
         d2, idx, self._knn_pairs = index.knn(K, pos_begin=lo, pos_end=hi, row_order=1, count_pairs=True)
@@ -334,44 +347,61 @@ class AstroLink:
         nat.scatter_rows(raw_all[sel].contiguous().view(-1, 1), perm, raw.view(-1, 1))
         return raw, kNN
 
-    def _sharded_knn_peer(self, index, w, rank, lo, hi, peer):
-        """Exchange fused into the kernels: every rank's kNN epilogue stores the k_link nearest ids, and
-        its density kernel the raw log-density, directly into rank 0's arrays (peer-mapped over NVLink)."""
+    def _sharded_knn_peer(self, w, rank):
+        """Exchange fused into the kernels: every searching rank's kNN epilogue stores the k_link nearest ids and the raw
+        log-density of its queries directly into rank 0's arrays (peer-mapped over NVLink), in index-position order.
+        The leaves are dealt to the ranks in chunks (dist.deal_chunks); rank 0, which also runs everything after the
+        exchange, takes a smaller share or none (dist.tail_aware_widths) -- with none it builds no index either, and the
+        first searching rank sends it the index permutation it needs to put the rows back into point order."""
+        from . import dist as adist
         n, K, L = self.n_samples, self.k_den, self.k_link
         dt = torch.float32 if self.P.dtype == np.float32 else torch.float64
-        from . import dist as adist
-        P_ = index.positions
+        peer = self._dist.peer
+        world = self._world()[1]
+        widths = self._dist.widths
+        P_ = nat.index_positions(n)
+        self._index_positions = P_
         half = peer.next_epoch()
         knn0 = peer.get(f"kNN_by_position_{half}", (P_, L), torch.int32, self._device)
         raw0 = peer.get(f"logRho_raw_by_position_{half}", (P_,), dt, self._device)
-        # The leaves are dealt to the ranks in chunks (evens out regional differences in search cost); every
-        # rank's rows go to rank 0 in index-position order, as full 128-byte stores from the kernels.
-        begin, chunk, stride, rows = adist.deal_chunks(P_, rank, self._world()[1], nat.LEAF)
-        a, b = self._stage("knn")
-        a.record()
-        if w is None:
-            # density fused into the search epilogue: both results go straight to rank 0 (position order)
-            _, _, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True, link_out=knn0,
-                                              want_idx=False, chunk=chunk, stride=stride, logrho_out=raw0,
-                                              d_intrinsic=self.d_intrinsic, want_d2=False)
+        perm0 = peer.get(f"perm_by_position_{half}", (P_,), torch.int32, self._device) if widths[0] == 0 else None
+        begin, chunk, stride, rows = adist.deal_chunks(P_, rank, world, nat.LEAF, widths=widths)
+        index = None
+        if widths[rank] > 0:
+            Pt = self._dev("P_transform")
+            if not Pt.is_contiguous():
+                Pt = Pt.contiguous()
+            a, b = self._stage("index_build")
+            a.record()
+            index = nat.Index(Pt)
             b.record()
-        else:
-            d2, idx, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True,
-                                                 link_out=knn0, want_idx=True, chunk=chunk, stride=stride)
-            b.record()
-            nat.logrho_dealt(d2, idx, K, self.d_intrinsic, begin, P_, chunk, stride, raw0, weights=w)
-            del d2, idx
+            a, b = self._stage("knn")
+            a.record()
+            if w is None:
+                # density fused into the search epilogue: both results go straight to rank 0 (position order)
+                _, _, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True, link_out=knn0,
+                                                  want_idx=False, chunk=chunk, stride=stride, logrho_out=raw0,
+                                                  d_intrinsic=self.d_intrinsic, want_d2=False)
+                b.record()
+            else:
+                d2, idx, self._knn_pairs = index.knn(K, pos_begin=begin, pos_end=P_, row_order=1, count_pairs=True,
+                                                     link_out=knn0, want_idx=True, chunk=chunk, stride=stride)
+                b.record()
+                nat.logrho_dealt(d2, idx, K, self.d_intrinsic, begin, P_, chunk, stride, raw0, weights=w)
+                del d2, idx
+            if perm0 is not None and rank == min(r for r in range(world) if widths[r] > 0):
+                nat.peer_copy(perm0, index.perm(), 4 * P_)
         a, b = self._stage("all_gather")
         a.record()
         torch.cuda.synchronize(self._device)      # this rank's peer stores are complete ...
         self._dist.barrier()                      # ... and so are everybody else's
         b.record()
         if rank != 0:
-            return torch.zeros((n,), dtype=dt, device=self._device), torch.zeros((1, L), dtype=torch.int32, device=self._device)
+            return torch.zeros((1,), dtype=dt, device=self._device), torch.zeros((1, L), dtype=torch.int32, device=self._device)
         # back to original point order (rank 0, local memory)
         a, b = self._stage("unpermute")
         a.record()
-        perm = index.perm()
+        perm = index.perm() if index is not None else perm0.tensor
         kNN = torch.empty((n, L), dtype=torch.int32, device=self._device)
         raw = torch.empty((n,), dtype=dt, device=self._device)
         nat.scatter_rows(knn0.tensor, perm, kNN)

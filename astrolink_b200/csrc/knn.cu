@@ -54,8 +54,8 @@ extern "C" int al_knn_density(const void* index, int64_t pos_begin, int64_t pos_
                               void* stream) {
     (void)ws; (void)ws_bytes;
     AL_REQUIRE(chunk_positions >= 0 && (chunk_positions == 0 || (chunk_positions % (LEAF * WARPS) == 0 && stride_positions >= chunk_positions &&
-               stride_positions % chunk_positions == 0)), AL_EINVAL,
-               "al_knn_dealt: chunk_positions must be a multiple of %d and stride_positions a multiple of chunk_positions", LEAF * WARPS);
+               stride_positions % (LEAF * WARPS) == 0)), AL_EINVAL,
+               "al_knn_dealt: chunk_positions and stride_positions must be multiples of %d, stride_positions >= chunk_positions", LEAF * WARPS);
     AL_REQUIRE(chunk_positions == 0 || row_order == 1, AL_EINVAL, "al_knn_dealt: dealt chunks need row_order 1");
     // link rows and fused densities: dealt launches (the sharded path) write them in index-position order, everything
     // else by original index

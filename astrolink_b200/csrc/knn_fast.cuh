@@ -63,21 +63,27 @@ struct Geo {
     static constexpr int MINB = D <= 8 ? KF_MINBLOCKS : (D <= 12 ? 4 : 3);
 };
 
-// per-warp shared memory (bytes from the warp's base):
-//   tile | queue [QC][32] u64 | heap pairs [K/2][32][2] u64 (node h's children in pair h; the root in a register) |
-//   query table [32][RS] f32 | own leaf box [D] (lo, hi) | spilled need masks [n_levels - 1][32] u32 | stack masks [8] | mbarrier
+// per-warp shared memory (bytes from the warp's base).  Everything except the heap's SIZE is a compile-time function of D, and
+// the heap comes last but one, so every address the hot loops use is the warp's base plus a constant (plus a lane term):
+//   tile | queue [QC][32] u64 | query table [32][RS] f32 | own leaf box [D] (lo, hi) | stack masks [8] | mbarrier |
+//   heap pairs [K/2][32][2] u64 (node h's children in pair h; the root in a register) | spilled need masks [n_levels - 1][32] u32
 __host__ __device__ static inline int spill_rows(int n_levels) { return n_levels > 1 ? n_levels - 1 : 1; }
 template <int D>
-static inline int warp_smem_bytes(int k, int n_levels) {
+struct Smem {
     typedef Geo<D> G;
-    size_t b = (size_t)G::TS;
-    b += (size_t)QC * 256;
+    static constexpr int QUEUE = G::TS;
+    static constexpr int QT = QUEUE + QC * 256;
+    static constexpr int QBOX = QT + 32 * G::RS * 4;
+    static constexpr int STK = QBOX + G::BS * 4;
+    static constexpr int BAR = STK + MAX_WIDE_LEVELS * 4;
+    static constexpr int HEAP = BAR + 16;
+    static_assert(HEAP % 16 == 0, "heap pairs are read with 128-bit loads");
+};
+template <int D>
+static inline int warp_smem_bytes(int k, int n_levels) {
+    size_t b = (size_t)Smem<D>::HEAP;
     b += (size_t)(k / 2) * 512;
-    b += (size_t)32 * G::RS * 4;
-    b += (size_t)G::BS * 4;
     b += (size_t)spill_rows(n_levels) * 128;
-    b += MAX_WIDE_LEVELS * 4;
-    b += 16;
     return (int)al_align(b, 16);      // d=6, k=20, 4 levels: 9 312 B -> 6 CTAs of 4 warps per SM
 }
 
@@ -188,15 +194,18 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     const int NP = K >> 1;                       // sibling pairs of the heap (node h's children live in pair h)
     const int n_levels = p.n_levels;
 
-    // ---- shared addresses
-    const u32 tile_sa = smem_u32(smem) + (u32)wib * (u32)p.warp_smem;      // the tile buffer
-    const u32 queue_sa = tile_sa + G::TS + (u32)lane * 8u;                 // this lane's queue slot 0 (slot stride 256)
-    const u32 pair_sa = tile_sa + G::TS + QC * 256u + (u32)lane * 16u;     // this lane's pair 0 (pair stride 512)
-    const u32 qt_sa = tile_sa + G::TS + QC * 256u + (u32)NP * 512u;        // query table
-    const u32 qbox_sa = qt_sa + 32u * G::RS * 4u;                          // own leaf's box, (lo_j, hi_j) pairs
-    const u32 need_sa = qbox_sa + G::BS * 4u + (u32)lane * 4u;             // spilled need masks, this lane's column (row stride 128)
-    const u32 stk_sa = qbox_sa + G::BS * 4u + (u32)spill_rows(n_levels) * 128u;    // children masks of the entries below the top
-    const u32 bar_sa = stk_sa + MAX_WIDE_LEVELS * 4u;                      // the tile buffer's mbarrier
+    // ---- shared addresses: the warp's base plus compile-time offsets (see Smem)
+    typedef Smem<D> S;
+    u32 tile_sa;                                                           // the tile buffer = the warp's base
+    // (opaque to the compiler: held in one register instead of being re-derived from %tid and the shared window in the loops)
+    asm volatile("mov.u32 %0, %1;" : "=r"(tile_sa) : "r"(smem_u32(smem) + (u32)wib * (u32)p.warp_smem));
+    const u32 queue_sa = tile_sa + S::QUEUE + (u32)lane * 8u;              // this lane's queue slot 0 (slot stride 256)
+    const u32 qt_sa = tile_sa + S::QT;                                     // query table
+    const u32 qbox_sa = tile_sa + S::QBOX;                                 // own leaf's box, (lo_j, hi_j) pairs
+    const u32 stk_sa = tile_sa + S::STK;                                   // children masks of the entries below the top
+    const u32 bar_sa = tile_sa + S::BAR;                                   // the tile buffer's mbarrier
+    const u32 pair_sa = tile_sa + S::HEAP + (u32)lane * 16u;               // this lane's pair 0 (pair stride 512)
+    const u32 need_sa = tile_sa + S::HEAP + (u32)NP * 512u + (u32)lane * 4u;   // spilled need masks, this lane's column (row stride 128)
     const u32 myrow_sa = qt_sa + (u32)lane * (G::RS * 4u);
 
     const u64 kinf = make_key(INFINITY, 0xffffffffu);

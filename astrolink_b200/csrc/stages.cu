@@ -790,6 +790,13 @@ extern "C" int al_peer_open(const unsigned char* handle64_host, void** ptr_host)
     *ptr_host = p;
     return AL_OK;
 }
+// device-to-device copy on `stream`; either pointer may be a peer-mapped buffer (al_peer_open)
+extern "C" int al_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    AL_REQUIRE(dst != nullptr && src != nullptr, AL_EINVAL, "al_peer_copy: bad arguments");
+    if (bytes == 0) return AL_OK;
+    AL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return AL_OK;
+}
 extern "C" int al_peer_release(void* ptr, int owner) {
     if (ptr == nullptr) return AL_OK;
     if (owner) AL_CUDA(cudaFree(ptr));

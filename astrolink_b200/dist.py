@@ -23,17 +23,41 @@ DEAL_CHUNK_LEAVES = 1024     # leaves per dealt chunk (32 768 points): small eno
                              # large enough that a chunk's candidate tiles stay hot in L2
 
 
-def deal_chunks(positions, rank, world, leaf=32, chunk_leaves=DEAL_CHUNK_LEAVES):
-    """Interleaved sharding for the peer-memory exchange: the spatial order is cut into chunks of
-    `chunk_leaves` leaves dealt round-robin, rank r owning chunks r, r + world, r + 2 world, ...
-    -> (begin, chunk, stride, rows): arguments of al_knn_dealt (index positions) and its number of output rows."""
+def tail_aware_widths(world):
+    """Shares of the search the ranks take, in dealt chunks per round of the deal.  Rank 0 also runs everything after the
+    exchange (edges, sort, aggregation, host statistics -- the globally ordered part, north-star item 4), about a quarter of
+    the single-GPU step, so it takes less of the search: 3 of 8 chunks on two GPUs, none from three GPUs up -- a dedicated
+    tail rank, so that run i's tail overlaps run i + 1's search on the other ranks (the peer buffers are double-buffered).
+    AL_TAIL_WIDTHS="w0,w1,..." overrides (development)."""
+    import os
+    env = os.environ.get("AL_TAIL_WIDTHS")
+    if env:
+        w = [int(x) for x in env.split(",")]
+        assert len(w) == world and sum(w) > 0 and min(w) >= 0
+        return w
+    if world == 1:
+        return [1]
+    if world == 2:
+        return [3, 5]
+    return [0] + [1] * (world - 1)
+
+
+def deal_chunks(positions, rank, world, leaf=32, chunk_leaves=DEAL_CHUNK_LEAVES, widths=None):
+    """Interleaved sharding for the peer-memory exchange: the spatial order is cut into chunks of `chunk_leaves` leaves
+    dealt in rounds; in every round rank r takes widths[r] consecutive chunks (default: one each -- r, r + world, ...).
+    -> (begin, chunk, stride, rows): arguments of al_knn_dealt (index positions) and its number of output rows; a rank of
+    width 0 gets chunk == rows == 0 (it does not search)."""
     n_leaves = positions // leaf
-    # small clouds: at least ~8 chunks per rank (chunks are whole CTAs of 4 leaves)
-    chunk_leaves = max(4, min(chunk_leaves, ((n_leaves + world * 8 - 1) // (world * 8) + 3) // 4 * 4))
-    chunk = chunk_leaves * leaf
-    stride = world * chunk
-    begin = rank * chunk
-    rows = 0 if begin >= positions else (positions - begin + stride - 1) // stride * chunk
+    widths = [1] * world if widths is None else list(widths)
+    assert len(widths) == world
+    total = sum(widths)
+    # small clouds: at least ~8 rounds (chunks are whole CTAs of 4 leaves)
+    chunk_leaves = max(4, min(chunk_leaves, ((n_leaves + total * 8 - 1) // (total * 8) + 3) // 4 * 4))
+    base = chunk_leaves * leaf
+    chunk = widths[rank] * base
+    stride = total * base
+    begin = sum(widths[:rank]) * base
+    rows = 0 if (chunk == 0 or begin >= positions) else (positions - begin + stride - 1) // stride * chunk
     return begin, chunk, stride, rows
 
 
@@ -98,11 +122,13 @@ class TorchDist:
     neighbour lists and densities are written by the kernels directly into rank 0's buffers through
     NVLink peer memory; peer=False: padded shards + NCCL all-gather."""
 
-    def __init__(self, group=None, peer=True):
+    def __init__(self, group=None, peer=True, widths=None):
         import torch.distributed as td
         self.td = td
         self.group = group
         self.peer = PeerBuffers(self) if peer else None
+        # shares of the search per rank (peer path): see tail_aware_widths
+        self.widths = list(widths) if widths is not None else tail_aware_widths(td.get_world_size(group))
 
     def get_rank(self):
         return self.td.get_rank(self.group)

@@ -319,7 +319,8 @@ def run_b200(args):
     ms_value, c, launches, steps_value = timed(True, args.steps)
     # ---- roofline inputs of the dominant kernel (kNN), from the last timed resident run
     stage = c.stage_ms()
-    pairs = int(c._knn_pairs[0].item())
+    pairs = int(c._knn_pairs[0].item()) if c._knn_pairs is not None else 0      # (a dedicated tail rank does not search)
+    stage.setdefault("knn", 0.0)
     host_timers = {k: round(1e3 * getattr(c, k), 2) for k in ("_transformTime", "_logRhoTime", "_aggregateTime", "_regrTime", "_rejTime", "_totalTime")}
     K, L = c.k_den, c.k_link
     n_groups, n_clusters = (int(c.groups.shape[0]), int(c.clusters.shape[0])) if rank == 0 else (0, 0)
@@ -333,7 +334,7 @@ def run_b200(args):
         tmax = t.clone()
         td.all_reduce(t, op=td.ReduceOp.SUM)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
-        tmin = torch.tensor([stage["knn"]], dtype=torch.float64, device=dev)
+        tmin = torch.tensor([stage["knn"] if stage["knn"] > 0 else 1e30], dtype=torch.float64, device=dev)
         td.all_reduce(tmin, op=td.ReduceOp.MIN)
         pairs_total, knn_ms, knn_ms_min = int(t[0].item()), float(tmax[1].item()), float(tmin[0].item())
     else:
@@ -357,8 +358,9 @@ def run_b200(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    flops = pairs * 3.0 * d                      # this rank's launch
-    achieved = flops / (stage["knn"] * 1e-3) / 1e12
+    # the dominant kernel's launch on this rank; when rank 0 is a dedicated tail rank, the job's pairs over the slowest launch
+    flops = (pairs if pairs > 0 else pairs_total / max(1, world - 1)) * 3.0 * d
+    achieved = flops / ((stage["knn"] if stage["knn"] > 0 else knn_ms) * 1e-3) / 1e12
     E = n * (L - 1)
     esz = P.dtype.itemsize
     tile_bytes = 32 * 4 + 16 * ((2 * d + 3) // 4 * 4) * esz + (2 * d * esz + 15) // 16 * 16
@@ -405,7 +407,8 @@ def run_b200(args):
         "metric": METRIC, "value": n / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_value, "ms_each_step": steps_value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k_den": K, "k_link": L,
-                   "parallelism": f"query-sharded x{world}, aggregation on rank 0" if world > 1 else "single GPU",
+                   "parallelism": (f"query-sharded x{world} (search shares per rank {D.widths}), aggregation on rank 0; consecutive runs "
+                                   f"pipeline: rank 0 finishes run i while the other ranks search run i+1") if world > 1 else "single GPU",
                    "l2": l2_note,
                    "groups": n_groups, "clusters": n_clusters},
         "result_checksum": checksum,
@@ -414,7 +417,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"kernel": f"kf::knn_fast_kernel<{d}>" if P.dtype == np.float32 else f"knn_kernel<double,{d}>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
-                     "pairs_evaluated": pairs, "flop_per_pair": 3 * d, "kernel_ms": stage["knn"],
+                     "pairs_evaluated": pairs if pairs > 0 else pairs_total, "flop_per_pair": 3 * d, "kernel_ms": stage["knn"] if stage["knn"] > 0 else knn_ms,
                      "brute_force_equiv_tflops": (float(n) * n * 3 * d) / (knn_ms * 1e-3) / 1e12 / world,
                      "peak_source": "FP32 FMA issue rate measured in this run (al_fp32_peak_tflops); MEASURED_PEAKS.json has no FP32 figure",
                      "ceiling_note": "SUB+FMA mix caps the flop fraction at 0.75 of FMA peak; the kernel is instruction-issue / latency bound "

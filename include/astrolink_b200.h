@@ -201,6 +201,9 @@ int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int col
 int al_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle64_host);
 int al_peer_open(const unsigned char* handle64_host, void** ptr_host);
 int al_peer_release(void* ptr, int owner);
+/* Device-to-device copy on `stream`; dst or src may be a buffer mapped with al_peer_open (multi-GPU path: the index
+ * permutation travels to the rank that un-permutes the neighbour rows). */
+int al_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 /* enables peer access from the current device to `peer_device` (idempotent). */
 int al_enable_peer_access(int peer_device);
 /* kernels launched by this library so far in this process (its own kernels; CUB's

@@ -93,3 +93,26 @@ def test_dealt_chunks_cover_every_position_once():
                 assert int(pos[0]) == begin and int(pos.max()) < positions + chunk
                 seen.index_add_(0, pos[pos < positions], torch.ones(int((pos < positions).sum()), dtype=torch.int32))
             assert bool((seen == 1).all()), (positions, world)
+
+
+def test_weighted_deal_covers_every_position_once():
+    """Tail-aware dealing (dist.tail_aware_widths): ranks take different numbers of chunks per round -- rank 0, which runs
+    the globally ordered tail, fewer or none -- and the positions are still covered exactly once."""
+    from astrolink_b200 import dist as adist
+    assert adist.tail_aware_widths(1) == [1] and adist.tail_aware_widths(2) == [3, 5]
+    assert adist.tail_aware_widths(4) == [0, 1, 1, 1] and adist.tail_aware_widths(8) == [0] + [1] * 7
+    for positions in (4000 // 32 * 32 + 32, 150016, 10_000_000 // 32 * 32 + 32):
+        for widths in ([3, 5], [0, 1, 1, 1], [0, 1, 1], [2, 0, 1], [0] + [1] * 7, [1, 4, 4, 4]):
+            world = len(widths)
+            seen = torch.zeros(positions, dtype=torch.int32)
+            for r in range(world):
+                begin, chunk, stride, rows = adist.deal_chunks(positions, r, world, widths=widths)
+                assert stride % (32 * 4) == 0 and chunk % (32 * 4) == 0
+                if widths[r] == 0:
+                    assert chunk == 0 and rows == 0
+                    continue
+                if rows == 0:
+                    continue
+                pos = adist.dealt_positions(begin, chunk, stride, rows, "cpu")
+                seen.index_add_(0, pos[pos < positions], torch.ones(int((pos < positions).sum()), dtype=torch.int32))
+            assert bool((seen == 1).all()), (positions, widths)

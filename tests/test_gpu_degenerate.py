@@ -65,11 +65,11 @@ def test_density_kernel_on_degenerate_rows(tag, rtol):
     assert np.all(np.abs(got[fin] - ref[fin]) <= 10 * rtol * np.maximum(np.abs(ref[fin]), 1e-30))
 
 
-def _cloud_with_copies(n, d, copies, dtype, seed=11):
+def _cloud_with_copies(n, d, copies, second, dtype, seed=11):
     rng = np.random.default_rng(seed)
     P = rng.normal(0, 1, (n, d))
-    P[:copies] = P[0]              # `copies` coincident points
-    P[copies:2 * copies - 3] = P[copies]        # a second stack, smaller than k_den
+    P[:copies] = P[0]                           # `copies` coincident points
+    P[copies:copies + second] = P[copies]       # a second, smaller stack
     return np.ascontiguousarray(P[rng.permutation(n)].astype(dtype))
 
 
@@ -82,7 +82,7 @@ def test_search_and_fused_density_with_coincident_points(dtype):
     from oracle import oracle
     nat.require_cuda()
     K = 12
-    P = _cloud_with_copies(4000, 3, K + 5, dtype)
+    P = _cloud_with_copies(4000, 3, K + 5, K - 3, dtype)      # the second stack is smaller than k_den: positive core distance
     index = nat.Index(torch.from_numpy(P).cuda())
     d2, idx = index.knn(K)
     od2, oidx = oracle.knn(P, K)
@@ -105,12 +105,12 @@ def test_run_with_coincident_points_documented_behaviour():
     ignored by the min/max and stay NaN; every stage completes; `ordering` is still a permutation and the group rows are
     well formed."""
     from astrolink_b200 import AstroLink
-    P = _cloud_with_copies(6000, 3, 30, np.float32)
+    P = _cloud_with_copies(6000, 3, 30, 27, np.float32)      # two stacks of >= k_den = 20 coincident points
     c = AstroLink(P)
     c.transform_data()
     c.estimate_density_and_kNN()
     lr = c.logRho.copy()
-    assert int(np.isnan(lr).sum()) == 30 + (30 - 3 >= c.k_den) * (30 - 3)
+    assert int(np.isnan(lr).sum()) == 30 + 27
     fin = lr[np.isfinite(lr)]
     assert fin.min() == 0.0 and 0.999 < fin.max() <= 1.0
     c.aggregate()
@@ -147,8 +147,11 @@ def test_edges_when_rows_lack_their_own_point():
     nat.require_cuda()
     rng = np.random.default_rng(4)
     n, L = 3000, 6
-    knn = rng.integers(0, n, (n, L)).astype(np.uint32)
-    knn[::3, 0] = np.arange(0, n, 3)          # a third of the rows contain themselves, the others (almost surely) do not
+    # rows of distinct ids, none equal to the row's own point ...
+    knn = (np.arange(n)[:, None] + 1 + np.stack([rng.permutation(n - 1)[:L] for _ in range(n)])) % n
+    assert (knn != np.arange(n)[:, None]).all()
+    knn = knn.astype(np.uint32)
+    knn[::3, 0] = np.arange(0, n, 3)          # ... except every third row, which holds itself first, as a search result does
     lr = rng.random(n).astype(np.float32)
     w, pairs = nat.make_edges(torch.from_numpy(lr).cuda(), torch.from_numpy(knn.view(np.int32)).cuda(), L)
     opairs, oedges = oracle.make_graph(lr, knn)

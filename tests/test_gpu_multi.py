@@ -33,8 +33,54 @@ for D in (adist.TorchDist(peer=True), adist.TorchDist(peer=False)):
             assert (c.logRho == s.logRho).all(), "logRho differs between sharded and single-GPU runs"
             assert (c.ordering == s.ordering).all() and (c.groups == s.groups).all()
             assert (c.clusters == s.clusters).all() and list(c.ids) == list(s.ids)
+# weighted densities (a5) with n % 32 != 0: padding rows of the last leaf must not be gathered through
+w = np.random.default_rng(3).uniform(0.5, 2.0, P.shape[0])
+sw = None
+if rank == 0:
+    sw = AstroLink(P, weights=w)
+    sw.run()
+for D in (adist.TorchDist(peer=True), adist.TorchDist(peer=False)):
+    c = AstroLink(P, weights=w, dist=D)
+    c.run()
+    if rank == 0:
+        assert (c.logRho == sw.logRho).all() and (c.ordering == sw.ordering).all() and (c.groups == sw.groups).all()
 if rank == 0:
     print("MULTI_OK", c.clusters.shape[0])
+td.destroy_process_group()
+'''
+
+# The same sharded code on ONE GPU: `world` processes share cuda:0 (gloo process group for the barrier and the handle
+# broadcast; the peer buffers are CUDA IPC mappings of rank 0's memory, here on the same device).  world 2: rank 0 takes
+# 3 of 8 chunks; world 3: rank 0 is a dedicated tail rank and gets the index permutation from rank 1.
+SCRIPT_ONE_GPU = r'''
+import os, sys
+sys.path.insert(0, os.environ["AL_ROOT"])
+import numpy as np, torch, torch.distributed as td
+from astrolink_b200 import AstroLink, synth
+from astrolink_b200 import dist as adist
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(0)
+td.init_process_group("gloo")
+for P, kw in ((synth.halo6d(150001, seed=9, n_sub=32), {}), (synth.gmm3d_nested(60013, seed=4), dict(adaptive=0)),
+              (synth.two_gaussians(20001, 2, 3, np.float64), {})):
+    s = None
+    w = np.random.default_rng(3).uniform(0.5, 2.0, P.shape[0])
+    D = adist.TorchDist(peer=True)
+    for weights in (None, w):
+        if rank == 0:
+            s = AstroLink(P, weights=weights, **kw)
+            s.run()
+        for rep in range(3):      # three runs: both halves of the double-buffered peer arrays, cached mappings
+            c = AstroLink(P, weights=weights, dist=D, **kw)
+            c.run()
+            if rank == 0:
+                assert (c.logRho == s.logRho).all(), "logRho differs between sharded and single-GPU runs"
+                assert (c.ordering == s.ordering).all() and (c.groups == s.groups).all()
+                assert (c.prominences == s.prominences).all()
+                assert (c.clusters == s.clusters).all() and list(c.ids) == list(s.ids)
+if rank == 0:
+    print("MULTI_OK widths", D.widths)
+td.barrier()
 td.destroy_process_group()
 '''
 
@@ -49,4 +95,17 @@ def test_sharded_run_equals_single_gpu(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_OK" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_run_on_one_gpu_equals_single_process(tmp_path, world):
+    """The sharded path without a second GPU: `world` processes on cuda:0 (see SCRIPT_ONE_GPU)."""
+    script = tmp_path / "multi1.py"
+    script.write_text(SCRIPT_ONE_GPU)
+    env = dict(os.environ, AL_ROOT=ROOT, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29741 + world), str(script)],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_OK" in r.stdout
