@@ -58,6 +58,8 @@ _SIGS = {
     "al_w1_workspace_bytes": (_sz, [_i64]),
     "al_w1_prepare": (_int, [_vp, _int, _i64, _int, _int, _vp, _sz, _vp, _vp]),
     "al_w1_eval": (_int, [_vp, _sz, _i64, _c.c_double, _c.c_double, _vp, _vp]),
+    "al_w1_batch_chunks": (_int, [_i64]),
+    "al_w1_eval_batch": (_int, [_vp, _sz, _i64, _vp, _int, _vp, _vp]),
     "al_significance": (_int, [_vp, _int, _i64, _c.c_double, _c.c_double, _vp, _vp]),
 }
 
@@ -364,11 +366,44 @@ class W1Objective:
         _check(L.al_w1_prepare(_ptr(prom), _dt(prom), self.G, prom.shape[1], col, _ptr(self.ws), self.ws.numel(),
                                self.sorted.ctypes.data_as(ctypes.c_void_p), _stream()), "al_w1_prepare")
         self._val = ctypes.c_double(0.0)
+        self._cache = {}
+        self.calls = self.hits = 0
 
     def __call__(self, p):
-        _check(lib().al_w1_eval(_ptr(self.ws), self.ws.numel(), self.G, float(p[0]), float(p[1]), ctypes.byref(self._val), _stream()),
-               "al_w1_eval")
-        return float(self._val.value)
+        """The objective at p.  SciPy's L-BFGS-B with jac='3-point' calls this at x and then at the finite-difference points
+        around x, one by one; the points around x are predicted here (same step rule as scipy.optimize's approx_derivative:
+        h = eps^(1/3) * max(1, |x|), central unless a bound is in the way) and evaluated in the same GPU call as x itself.
+        A value is only ever returned for exactly the point asked for, so a wrong prediction costs a cache miss, nothing else."""
+        key = (float(p[0]), float(p[1]))
+        v = self._cache.get(key)
+        if v is not None:
+            self.hits += 1
+            return v
+        pts = [key] + [q for q in self._around(key) if q != key]
+        ab = np.asarray(pts, dtype=np.float64)
+        out = np.empty(len(pts), dtype=np.float64)
+        _check(lib().al_w1_eval_batch(_ptr(self.ws), self.ws.numel(), self.G, ab.ctypes.data_as(ctypes.c_void_p), len(pts),
+                                      out.ctypes.data_as(ctypes.c_void_p), _stream()), "al_w1_eval_batch")
+        self._cache = {q: float(o) for q, o in zip(pts, out)}
+        self.calls += 1
+        return self._cache[key]
+
+    _H = np.finfo(np.float64).eps ** (1.0 / 3.0)
+
+    def _around(self, x, lb=1.0):
+        """The points scipy's 3-point scheme evaluates around x for the bounds ((1, inf), (1, inf)) of the fit."""
+        pts = []
+        for i in (0, 1):
+            h = self._H * max(1.0, abs(x[i]))
+            if x[i] - h >= lb:                       # central
+                steps = (-h, h)
+            else:                                    # one-sided, away from the lower bound
+                steps = (h, 2.0 * h)
+            for st in steps:
+                q = list(x)
+                q[i] = x[i] + st
+                pts.append((q[0], q[1]))
+        return pts
 
 
 def launch_count():

@@ -746,6 +746,104 @@ extern "C" int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double
     return AL_OK;
 }
 
+// ---- batched evaluation: B parameter pairs per call, two launches and one host read for all of them.
+// SciPy's L-BFGS-B with jac='3-point' evaluates the objective at x and at 2 d points around it, one call at a time; the
+// host wrapper predicts those points and asks for all of them at once (a wrong prediction only costs a cache miss).
+// The range of gaps is cut into chunks; pass 1 sums the probability mass of every chunk, pass 2 re-derives the masses of
+// its chunk on top of the preceding chunks' total (no global scan) and integrates |cdf - empirical cdf|.  All sums run in
+// a fixed order, so a given (a, b) always yields the same bits.
+constexpr int W1B_THREADS = 256;
+constexpr int W1B_MAX = 16;          // parameter pairs per call
+
+struct W1Batch { double am1[W1B_MAX], bm1[W1B_MAX], lbeta[W1B_MAX]; };
+
+template <bool DIST>
+__global__ void __launch_bounds__(W1B_THREADS) w1_batch_kernel(const double* __restrict__ log_mid, const double* __restrict__ log_omm,
+                                                               const double* __restrict__ widths, i64 G, i64 chunk, int n_chunks,
+                                                               W1Batch prm, double q0, double qstep,
+                                                               const double* __restrict__ chunk_mass, double* __restrict__ out) {
+    const int c = blockIdx.x, b = blockIdx.y;
+    const i64 lo = (i64)c * chunk, hi = lo + chunk < G ? lo + chunk : G;
+    const i64 per = (chunk + W1B_THREADS - 1) / W1B_THREADS;
+    const i64 t0 = lo + (i64)threadIdx.x * per, t1 = t0 + per < hi ? t0 + per : hi;
+    const double am1 = prm.am1[b], bm1 = prm.bm1[b], lbeta = prm.lbeta[b];
+    double local = 0.0;
+    for (i64 i = t0; i < t1; i++) local += exp(am1 * log_mid[i] + bm1 * log_omm[i] - lbeta) * widths[i];
+    __shared__ double sm[W1B_THREADS];
+    sm[threadIdx.x] = local;
+    __syncthreads();
+    if (!DIST) {
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int k = 0; k < W1B_THREADS; k++) v += sm[k];
+            out[(i64)b * n_chunks + c] = v;
+        }
+        return;
+    }
+    // mass before this thread's items: the preceding chunks (fixed order), then the preceding threads of this chunk
+    double before = 0.0;
+    for (int k = 0; k < c; k++) before += chunk_mass[(i64)b * n_chunks + k];
+    for (int k = 0; k < (int)threadIdx.x; k++) before += sm[k];
+    double cdf = before, acc = 0.0;
+    for (i64 i = t0; i < t1; i++) {
+        const double w = widths[i];
+        cdf += exp(am1 * log_mid[i] + bm1 * log_omm[i] - lbeta) * w;
+        acc += fabs(cdf - (q0 + (double)i * qstep)) * w;
+    }
+    __syncthreads();
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int k = 0; k < W1B_THREADS; k++) v += sm[k];
+        out[(i64)b * n_chunks + c] = v;
+    }
+}
+
+extern "C" int al_w1_batch_chunks(int64_t G) {
+    i64 c = (G + 4095) / 4096;
+    if (c < 1) c = 1;
+    if (c > 128) c = 128;
+    return (int)c;
+}
+
+extern "C" int al_w1_eval_batch(void* ws, size_t ws_bytes, int64_t G, const double* ab_host, int B, double* values_host, void* stream) {
+    AL_REQUIRE(G >= 1 && ab_host != nullptr && values_host != nullptr && B >= 1 && B <= W1B_MAX, AL_EINVAL, "al_w1_eval_batch: bad arguments");
+    W1Ws w;
+    AL_REQUIRE(w1_layout(ws, ws_bytes, G, &w), AL_ENOMEM, "al_w1_eval_batch: workspace too small");
+    const int n_chunks = al_w1_batch_chunks(G);
+    // scratch: the mass / keys_in arrays of the workspace (G doubles each) are free between evaluations
+    AL_REQUIRE((i64)B * n_chunks <= G, AL_EINVAL, "al_w1_eval_batch: G too small for the batched path (use al_w1_eval)");
+    double* chunk_mass = w.mass;
+    double* chunk_dist = w.keys_in;
+    W1Batch prm;
+    for (int b = 0; b < B; b++) {
+        const double a = ab_host[2 * b], bb = ab_host[2 * b + 1];
+        AL_REQUIRE(a > 0.0 && bb > 0.0, AL_EINVAL, "al_w1_eval_batch: parameters must be positive");
+        prm.am1[b] = a - 1.0;
+        prm.bm1[b] = bb - 1.0;
+        prm.lbeta[b] = lgamma(a) + lgamma(bb) - lgamma(a + bb);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 chunk = (G + n_chunks - 1) / n_chunks;
+    const double half = 1.0 / (2.0 * (double)G);
+    const double qstep = G > 1 ? (1.0 - 2.0 * half) / (double)(G - 1) : 0.0;
+    dim3 grid((unsigned)n_chunks, (unsigned)B);
+    w1_batch_kernel<false><<<grid, W1B_THREADS, 0, st>>>(w.log_mid, w.log_omm, w.widths, G, chunk, n_chunks, prm, half, qstep, nullptr, chunk_mass);
+    AL_CHECK_LAUNCH();
+    w1_batch_kernel<true><<<grid, W1B_THREADS, 0, st>>>(w.log_mid, w.log_omm, w.widths, G, chunk, n_chunks, prm, half, qstep, chunk_mass, chunk_dist);
+    AL_CHECK_LAUNCH();
+    double part[W1B_MAX * 128];
+    AL_CUDA(cudaMemcpyAsync(part, chunk_dist, sizeof(double) * (size_t)B * n_chunks, cudaMemcpyDeviceToHost, st));
+    AL_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; b++) {
+        double v = 0.0;
+        for (int c = 0; c < n_chunks; c++) v += part[(size_t)b * n_chunks + c];
+        values_host[b] = v;
+    }
+    return AL_OK;
+}
+
 // peer access from the current device to `peer_device` (multi-GPU path: kernels on rank r store into rank 0's buffers)
 extern "C" int al_enable_peer_access(int peer_device) {
     int dev = 0;

@@ -183,7 +183,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict__ P, const u32* __restrict__ perm,
                                                              const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
                                                              const int* __restrict__ sdim, const float* __restrict__ slo,
-                                                             const float* __restrict__ sscale, u32* keys, i64 n, int d, int cbits) {
+                                                             const float* __restrict__ sscale, const u32* __restrict__ noderank,
+                                                             u32* keys, i64 n, int d, int cbits) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const i64 leaf = p / LEAF;
@@ -200,7 +201,14 @@ __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict
     } else {
         low = (u32)(p - leaf * LEAF);
     }
-    keys[p] = (a << cbits) | low;
+    // nodes are numbered in order (rank of their first leaf among the node starts): a round that has made 2^L nodes so far
+    // needs only L node bits in the key, so the early rounds sort fewer digits
+    keys[p] = (noderank[a] << cbits) | low;
+}
+
+__global__ void __launch_bounds__(256) tree_node_start_kernel(const u32* __restrict__ nodeA, u32* __restrict__ flag, i64 n_leaves) {
+    i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_leaves) flag[l] = nodeA[l] == (u32)l ? 1u : 0u;
 }
 
 // After a round's sort every node is ordered along its widest axis, so the same order serves `levels`
@@ -438,15 +446,17 @@ struct BuildWs {
     u32 *bbox_lo, *bbox_hi;
     int* sdim;
     float *slo, *sscale;
+    u32 *nflag, *nrank;
     void* cub_tmp;
     size_t cub_bytes;
 };
 
 static size_t sort_temp_bytes(i64 n) {
-    size_t bytes = 0;
+    size_t bytes = 0, scan = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
                                     (i64)n, 0, 32, (cudaStream_t)0);
-    return bytes;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (const u32*)nullptr, (u32*)nullptr, (i64)((n + LEAF - 1) / LEAF), (cudaStream_t)0);
+    return bytes > scan ? bytes : scan;       // the same buffer serves the sorts and the node-rank scans
 }
 
 extern "C" size_t al_index_bytes(int dtype, int64_t n, int d) {
@@ -473,6 +483,8 @@ extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
     s.add<int>(n_leaves);
     s.add<float>(n_leaves);
     s.add<float>(n_leaves);
+    s.add<u32>(n_leaves);
+    s.add<u32>(n_leaves);
     s.add<char>(sort_temp_bytes(n));
     return s.off + 256;
 }
@@ -493,6 +505,8 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     w.sdim = ar.get<int>(n_leaves);
     w.slo = ar.get<float>(n_leaves);
     w.sscale = ar.get<float>(n_leaves);
+    w.nflag = ar.get<u32>(n_leaves);
+    w.nrank = ar.get<u32>(n_leaves);
     w.cub_bytes = sort_temp_bytes(n);
     w.cub_tmp = ar.get<char>(w.cub_bytes);
     AL_REQUIRE(ar.ok, AL_ENOMEM, "al_index_build: workspace too small (%zu bytes given)", ws_bytes);
@@ -531,6 +545,7 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     if (cbits > 16) cbits = 16;
     if (const char* e = getenv("AL_TREE_CBITS")) { int v = atoi(e); if (v >= 3 && v <= cbits) cbits = v; }   // development knob
     AL_REQUIRE(cbits >= 5, AL_EINVAL, "al_index_build: too many leaves for 32-bit sort keys");
+    int levels_done = 0;
     for (int r = 0; r < rounds; r++) {
         AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
         AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
@@ -541,12 +556,19 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
         tree_node_split_info_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, w.sdim,
                                                                                        w.slo, w.sscale, n_leaves, d, cbits);
         AL_CHECK_LAUNCH();
+        // node ranks: an exclusive sum over the node-start flags of the leaves
+        tree_node_start_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nflag, n_leaves);
+        AL_CHECK_LAUNCH();
+        size_t sb = w.cub_bytes;
+        AL_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, sb, w.nflag, w.nrank, n_leaves, st));
         tree_make_keys_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            P, vals[cur], w.nodeA, w.nodeB, w.sdim, w.slo, w.sscale, keys[cur], n, d, cbits);
+            P, vals[cur], w.nodeA, w.nodeB, w.sdim, w.slo, w.sscale, w.nrank, keys[cur], n, d, cbits);
         AL_CHECK_LAUNCH();
         size_t tb = w.cub_bytes;
+        int rank_bits = levels_done < node_bits ? levels_done : node_bits;      // at most 2^levels_done nodes exist
         AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
-                                                cbits + node_bits, st));
+                                                cbits + rank_bits, st));
+        levels_done += sched[r];
         cur ^= 1;
         tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves, sched[r]);
         AL_CHECK_LAUNCH();

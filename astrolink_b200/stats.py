@@ -20,7 +20,8 @@ def _initial_beta_guess(p_sorted):
     N = p_sorted.size
     iqr = p_sorted[3 * N // 4] - p_sorted[N // 4]
     binwidth = 2.0 * iqr * N ** (-1.0 / 3.0)
-    counts = np.bincount(np.floor_divide(p_sorted, binwidth).astype(np.int64))
+    # (floor of the quotient, as numba's fastmath `//` in the reference; np.floor_divide is ten times slower on floats)
+    counts = np.bincount(np.floor(p_sorted / binwidth).astype(np.int64))
     mode = binwidth * (np.argmax(counts) + 0.5)
     mu = p_sorted.mean()
     var = p_sorted.var()

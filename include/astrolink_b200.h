@@ -188,6 +188,12 @@ size_t al_w1_workspace_bytes(int64_t G);
 int al_w1_prepare(const void* prominences, int dtype, int64_t G, int stride, int col, void* ws, size_t ws_bytes,
                   double* sorted_host, void* stream);
 int al_w1_eval(void* ws, size_t ws_bytes, int64_t G, double a, double b, double* value_host, void* stream);
+/* The same objective at B <= 16 parameter pairs (ab_host: B x {a, b}) in one call: two launches and one host read for
+ * all of them -- the optimiser's finite-difference points are evaluated together with the point itself.  Needs
+ * G >= 16 * al_w1_batch_chunks(G).  Sums run in a fixed order: a given (a, b) always yields the same value, whichever
+ * batch it is part of. */
+int al_w1_batch_chunks(int64_t G);
+int al_w1_eval_batch(void* ws, size_t ws_bytes, int64_t G, const double* ab_host, int B, double* values_host, void* stream);
 
 /* ---- helpers ------------------------------------------------------------ */
 /* scatter rows: dst[perm[p]][0..cols) = src[p][0..cols) for p in [0, rows), skipping
