@@ -30,6 +30,7 @@ _SIGS = {
     "al_index_build": (_int, [_vp, _int, _i64, _int, _vp, _sz, _vp, _sz, _vp]),
     "al_index_positions": (_i64, [_i64]),
     "al_index_perm": (_vp, [_vp]),
+    "al_index_release": (None, [_vp]),
     "al_knn_workspace_bytes": (_sz, [_int, _i64, _int, _int]),
     "al_knn": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "al_logrho": (_int, [_vp, _vp, _vp, _int, _i64, _int, _int, _vp, _vp]),
@@ -42,7 +43,7 @@ _SIGS = {
     "al_aggregate_workspace_bytes": (_sz, [_int, _i64, _i64]),
     "al_aggregate": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "al_scatter_rows": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
-    "al_fp32_peak_tflops": (_int, [_vp, _vp]),
+    "al_fp32_peak_tflops": (_int, [_vp, _vp, _sz, _vp]),
     "al_launch_count": (_i64, []),
     "al_peer_alloc": (_int, [_sz, _vp, _vp]),
     "al_peer_open": (_int, [_vp, _vp]),
@@ -152,6 +153,15 @@ class Index:
         _check(L.al_index_build(_ptr(Pt), _dt(Pt), self.n, self.d, _ptr(self.buf), self.buf.numel(), _ptr(ws), ws.numel(),
                                 _stream()), "al_index_build")
         self.positions = int(L.al_index_positions(self.n))
+
+    def __del__(self):
+        # the library caches the index header per device pointer: drop the entry before the caching allocator can hand the
+        # same address to another buffer
+        try:
+            if _lib is not None and getattr(self, "buf", None) is not None:
+                _lib.al_index_release(_ptr(self.buf))
+        except Exception:
+            pass
 
     def perm(self):
         """index position -> original point (uint32 viewed as int32 tensor; padding = -1)."""
@@ -341,7 +351,8 @@ def scatter_rows(src, perm, dst):
 def fp32_peak_tflops():
     L = lib()
     v = ctypes.c_double(0.0)
-    _check(L.al_fp32_peak_tflops(ctypes.byref(v), _stream()), "al_fp32_peak_tflops")
+    scratch = torch.empty(64, dtype=torch.uint8, device="cuda")
+    _check(L.al_fp32_peak_tflops(ctypes.byref(v), _ptr(scratch), scratch.numel(), _stream()), "al_fp32_peak_tflops")
     return float(v.value)
 
 

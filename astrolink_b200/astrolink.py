@@ -119,6 +119,8 @@ class AstroLink:
         nat.require_cuda()
         nat.lib()
         assert self.n_samples < 2 ** 31 - 1, "astrolink_b200 supports up to 2**31 - 2 points (uint32 indices)"
+        assert self.n_samples * (self.k_link - 1) < 2 ** 32 - 1, \
+            "astrolink_b200 supports up to 2**32 - 2 graph edges (n_samples * (k_link - 1)): edge ranks are uint32"
         assert self.P.dtype in (np.float32, np.float64), "astrolink_b200 supports float32 / float64 input"
         assert self.d_features <= 16, "astrolink_b200 supports up to 16 features in this release"
         assert self.k_den <= 128, "astrolink_b200 supports k_den <= 128 in this release"
@@ -456,6 +458,7 @@ class AstroLink:
             # small results first: the fit only waits for them, the large copies run underneath it
             for name in ("groups", "prominences", "ordering", "logRho"):
                 d = self.__dict__["_d_" + name]
+                d.record_stream(side)          # the copy reads d on the side stream: keep its memory until then
                 h = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
                 h.copy_(d, non_blocking=True)
                 bufs[name] = h
@@ -476,7 +479,9 @@ class AstroLink:
             h = bufs.pop(name).numpy()
             if name in ("groups", "ordering"):
                 h = h.view(np.uint32)
-            self.__dict__["_h_" + name] = h
+            # (an attribute the user has assigned or deleted in the meantime keeps the user's value)
+            if ("_d_" + name) in self.__dict__ and ("_h_" + name) not in self.__dict__:
+                self.__dict__["_h_" + name] = h
         if not bufs:
             self._pending = None
 

@@ -51,6 +51,16 @@ AGG_HD inline u32 agg_atomic_min(u32* p, u32 v) {
 #endif
 }
 
+AGG_HD inline u32 agg_atomic_or(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    return atomicOr(p, v);
+#else
+    u32 o = *p;
+    *p = o | v;
+    return o;
+#endif
+}
+
 // plain load the compiler may not hoist or fuse (values other threads are updating: pointer jumping)
 AGG_HD inline u32 agg_load_relaxed(const u32* p) { return *(const volatile u32*)p; }
 

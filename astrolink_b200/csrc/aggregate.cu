@@ -3,6 +3,9 @@
 // (reference astrolink/astrolink.py:384-604).
 #include <cub/cub.cuh>
 
+#include <iterator>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "aggregate_impl.h"
 #include "common.cuh"
 #include <stdlib.h>
@@ -19,6 +22,33 @@ __global__ void __launch_bounds__(256) agg_kernel_if(const u32* flag, i64 n, F f
     if (flag != nullptr && *flag == 0u) return;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) f(i);
 }
+
+// ---- stable selection through cub::DeviceSelect::If: the "items" are the indices 0..n-1, the output iterator hands
+// (index, position among the selected) to the caller's emit functor instead of storing anything itself
+template <class Emit>
+struct AggEmitProxy {
+    Emit emit;
+    i64 pos;
+    __host__ __device__ const AggEmitProxy& operator=(u32 idx) const { emit((i64)idx, pos); return *this; }
+};
+template <class Emit>
+struct AggEmitIterator {
+    typedef std::random_access_iterator_tag iterator_category;
+    typedef u32 value_type;
+    typedef i64 difference_type;
+    typedef void pointer;
+    typedef AggEmitProxy<Emit> reference;
+    Emit emit;
+    i64 base;
+    __host__ __device__ AggEmitProxy<Emit> operator[](i64 k) const { return AggEmitProxy<Emit>{emit, base + k}; }
+    __host__ __device__ AggEmitProxy<Emit> operator*() const { return AggEmitProxy<Emit>{emit, base}; }
+    __host__ __device__ AggEmitIterator operator+(i64 k) const { return AggEmitIterator{emit, base + k}; }
+};
+template <class Pred>
+struct AggPredOp {
+    Pred pred;
+    __host__ __device__ bool operator()(const u32& i) const { return pred((i64)i); }
+};
 
 __global__ void agg_fill_kernel(u32* p, u32 v, i64 n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
@@ -53,6 +83,22 @@ struct CudaExec {
         agg_kernel_if<Tag, F><<<(unsigned)g, 256, 0, st>>>(flag, n, f);
         note(cudaGetLastError());
         launches++;
+    }
+    // for every i in [0, n) with pred(i), in order: emit(i, rank of i among the selected); the count goes to count_dev[0]
+    template <class Tag, class Pred, class Emit>
+    void select(i64 n, Pred pred, Emit emit, u32* count_dev, AggArena& ar) {
+        if (n <= 0) { note(cudaMemsetAsync(count_dev, 0, 4, st)); return; }
+        const size_t mk = ar.mark();
+        thrust::counting_iterator<u32> in(0u);
+        AggEmitIterator<Emit> out{emit, 0};
+        AggPredOp<Pred> op{pred};
+        size_t tb = 0;
+        note(cub::DeviceSelect::If(nullptr, tb, in, out, count_dev, n, op, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DeviceSelect::If(tmp, tb, in, out, count_dev, n, op, st));
+        launches++;
+        ar.reset(mk);
     }
     void fill_u32(u32* p, u32 v, i64 n) {
         if (n <= 0) return;

@@ -147,14 +147,13 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         u32* hook = ar.get<u32>(N);
         u32* flag = ar.get<u32>(N + 1);
         u32* newid = ar.get<u32>(N + 1);
-        u32* pickflag = ar.get<u32>(m + 1);
-        u32* pkpos = ar.get<u32>(m + 1);
+        u32* pickbits = ar.get<u32>(m / 32 + 2);     // one bit per edge of the list: picked by a component this round
         u32* changed = ar.get<u32>(8);
         if (!ar.ok) return -2;
         if (node_off + N > nodefirst_cap) return -2;
         u32* nodefirst = nodefirst_all + node_off;
         x.fill_u32(first, NONE, N);
-        x.fill_u32(pickflag, 0, m + 1);
+        x.fill_u32(pickbits, 0, m / 32 + 2);
         {
             const uint2_agg* e_ = ep;
             x.template launch<TagPickFirst>(m, AGG_LAMBDA(i64 i) {
@@ -171,7 +170,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 u32 other = e.x == (u32)s ? e.y : e.x;
                 bool mutual = first[other] == i;
                 hook[s] = (mutual && (u32)s < other) ? (u32)s : other;
-                pickflag[i] = 1;
+                agg_atomic_or(pickbits + (i >> 5), 1u << (i & 31u));
             });
         }
         // Pointer jumping to the component roots.  Every vertex chases its pointer up to 24 hops and stores where it got
@@ -204,47 +203,41 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         // label[s] kept in flag[]
         x.template launch<TagLabel>(N, AGG_LAMBDA(i64 s) { flag[s] = newid[hook[s]]; });
         const u32* label = flag;
-        x.exclusive_sum_u32(pickflag, pkpos, m, ar, tot + 1);
         // every picked edge merges two components, so M + cnt = n - Nn <= n: the records below stay inside pk_*[n]
         {
             const uint2_agg* e_ = ep;
             const u32* r_ = er;
             const i64 M_ = M;
-            // one pass over the edge list: record the picked edges, and flag the survivors for the next level
-            // (not picked, endpoints in different new components); the keep flag overwrites the pick flag
-            u32* keep = pickflag;
-            x.template launch<TagRecord>(m, AGG_LAMBDA(i64 i) {
+            // Two stable single-pass selections over the edge list (no flag arrays, no prefix sums of them):
+            // (1) the picked edges, in list (= rank) order, become this level's records; the vertices that picked an edge
+            //     learn where it went (nodefirst);
+            x.fill_u32(nodefirst, NONE, N);
+            x.template select<TagRecord>(m, AGG_LAMBDA(i64 i) { return ((pickbits[i >> 5] >> (i & 31)) & 1u) != 0u; }, AGG_LAMBDA(i64 i, i64 pos) {
                 const uint2_agg e = e_[i];
-                const u32 lx = label[e.x], ly = label[e.y];
-                if (pickflag[i]) {
-                    const i64 c = M_ + pkpos[i];
-                    pk_rank[c] = r_ ? r_[i] : (u32)i;
-                    pk_K[c] = lx;
-                    pk_p0node[c] = e.x;
-                    const bool fx = first[e.x] == (u32)i, fy = first[e.y] == (u32)i;
-                    pk_picker[c] = (fx && fy) ? NONE : (fx ? e.x : e.y);
-                    keep[i] = 0u;
-                } else {
-                    keep[i] = lx != ly ? 1u : 0u;
-                }
-            });
-            x.template launch<TagNodeFirst>(N, AGG_LAMBDA(i64 s) {
-                u32 i = first[s];
-                nodefirst[s] = i == NONE ? NONE : (u32)(M_ + pkpos[i]);
-            });
-            x.exclusive_sum_u32(keep, pkpos, m, ar, tot + 2);
+                const i64 c = M_ + pos;
+                pk_rank[c] = r_ ? r_[i] : (u32)i;
+                pk_K[c] = label[e.x];
+                pk_p0node[c] = e.x;
+                const bool fx = first[e.x] == (u32)i, fy = first[e.y] == (u32)i;
+                pk_picker[c] = (fx && fy) ? NONE : (fx ? e.x : e.y);
+                if (fx) nodefirst[e.x] = (u32)c;
+                if (fy) nodefirst[e.y] = (u32)c;
+            }, tot + 1, ar);
+            // (2) the survivors -- not picked, endpoints in different new components -- relabelled, form the next level's list.
             uint2_agg* eo = ep_next;
             u32* ro = er_next;
-            x.template launch<TagCompact>(m, AGG_LAMBDA(i64 i) {
-                if (!keep[i]) return;
-                uint2_agg e = e_[i];
-                const u32 o = pkpos[i];
+            x.template select<TagCompact>(m, AGG_LAMBDA(i64 i) {
+                if ((pickbits[i >> 5] >> (i & 31)) & 1u) return false;
+                const uint2_agg e = e_[i];
+                return label[e.x] != label[e.y];
+            }, AGG_LAMBDA(i64 i, i64 pos) {
+                const uint2_agg e = e_[i];
                 uint2_agg ne;
                 ne.x = label[e.x];
                 ne.y = label[e.y];
-                eo[o] = ne;
-                ro[o] = r_ ? r_[i] : (u32)i;
-            });
+                eo[pos] = ne;
+                ro[pos] = r_ ? r_[i] : (u32)i;
+            }, tot + 2, ar);
             // the round's only host read: components, picked edges and surviving edges
             u32 h3[3];
             x.read_u32s(tot, h3, 3);
@@ -475,7 +468,6 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
     u32* wts = ar.get<u32>(TL);           // +w at enter, -w at exit, in tour order
     u32* wscan = ar.get<u32>(TL);
     u32* start_int = ar.get<u32>(M);
-    u32* start_leaf = ar.get<u32>(n);
     if (!ar.ok) return -2;
     const uint2_agg* rk = la;
     x.template launch<TagSizes>(M, AGG_LAMBDA(i64 c) {
@@ -534,15 +526,18 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
         });
         x.inclusive_sum_u32(wts, wscan, TL, ar);
         x.template launch<TagStarts>(M, AGG_LAMBDA(i64 c) { start_int[c] = wscan[(u32)(TL - 1) - rk[2 * c].y]; });
-        x.template launch<TagStarts>(n, AGG_LAMBDA(i64 v) {
-            const u32 P = nf0[v];
-            const u32 k0 = child0[P], k1 = child1[P];
-            const u32 s0 = node_size(k0), s1 = node_size(k1);
-            const u32 firstc = s0 >= s1 ? k0 : k1;
-            start_leaf[v] = start_int[P] + (firstc == (u32)v ? 0u : (s0 >= s1 ? s0 : s1));
-        });
     }
-    x.template launch<TagOrdering>(n, AGG_LAMBDA(i64 v) { ordering_out[start_leaf[v]] = (u32)v; });
+    // A leaf's place in the ordering follows from its parent node: the larger child (tie: child 0) starts where the node
+    // starts, the other one right after it.  One pass over the internal nodes (sequential reads of their children and
+    // starts) instead of one over the leaves (six random gathers each).
+    x.template launch<TagOrdering>(M, AGG_LAMBDA(i64 c) {
+        const u32 k0 = child0[c], k1 = child1[c];
+        if (k0 >= (u32)n && k1 >= (u32)n) return;
+        const u32 s0 = node_size(k0), s1 = node_size(k1);
+        const u32 st = start_int[c];
+        if (k0 < (u32)n) ordering_out[st + (s0 >= s1 ? 0u : s1)] = k0;
+        if (k1 < (u32)n) ordering_out[st + (s0 >= s1 ? s0 : 0u)] = k1;
+    });
 
     x.phase("B-rows");
     // ---- range-max tree over logRho in final order

@@ -525,13 +525,13 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, float a, fl
     if (s == 12345.678f) out[0] = s;
 }
 
-extern "C" int al_fp32_peak_tflops(double* tflops_host, void* stream) {
+extern "C" int al_fp32_peak_tflops(double* tflops_host, void* scratch, size_t scratch_bytes, void* stream) {
+    AL_REQUIRE(tflops_host != nullptr && scratch != nullptr && scratch_bytes >= 4, AL_EINVAL, "al_fp32_peak_tflops: needs 4 bytes of device scratch");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     AL_CUDA(cudaGetDevice(&dev));
     AL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    float* out = nullptr;
-    AL_CUDA(cudaMalloc(&out, 4));   // probe only; not on the hot path
+    float* out = (float*)scratch;
     cudaEvent_t e0, e1;
     AL_CUDA(cudaEventCreate(&e0));
     AL_CUDA(cudaEventCreate(&e1));
@@ -549,7 +549,6 @@ extern "C" int al_fp32_peak_tflops(double* tflops_host, void* stream) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(out);
     *tflops_host = best;
     return AL_OK;
 }

@@ -35,6 +35,10 @@ void index_register(const void* index, const IndexHeader& h) {
     std::lock_guard<std::mutex> lk(g_reg_mu);
     g_reg[index] = h;
 }
+extern "C" void al_index_release(const void* index) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_reg.erase(index);
+}
 
 // ---------------------------------------------------------------------------
 __host__ __device__ static inline u32 split_mid(u32 a, u32 b) {

@@ -65,6 +65,10 @@ int al_index_build(const void* Pt, int dtype, int64_t n, int d, void* index, siz
  * original-index permutation (device, uint32[al_index_positions], padding = 0xffffffff) */
 int64_t al_index_positions(int64_t n);
 const uint32_t* al_index_perm(const void* index);
+/* Forget the host-side copy of an index header (the library caches it per device pointer so that al_knn need not read
+ * it back from the device); call before the index buffer is freed or reused for anything but a rebuild (al_index_build
+ * replaces the entry of its buffer).  Unknown pointers are ignored. */
+void al_index_release(const void* index);
 
 /* ---- a3: KDTree.query(P_t, k=k_den, sqr_dists=True) (astrolink.py:279) ---
  * Exact k nearest neighbours (self included) of the points at index positions
@@ -216,8 +220,9 @@ int al_enable_peer_access(int peer_device);
  * internal launches are not counted). */
 int64_t al_launch_count(void);
 /* measured FP32 FMA issue rate of this GPU in TFLOP/s (2 flop per FMA); used as
- * the roofline denominator of the kNN kernel.  Synchronous. */
-int al_fp32_peak_tflops(double* tflops_host, void* stream);
+ * the roofline denominator of the kNN kernel.  Synchronous.  `scratch`: >= 4 bytes of
+ * caller-owned device memory (like every entry point, this one allocates nothing). */
+int al_fp32_peak_tflops(double* tflops_host, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

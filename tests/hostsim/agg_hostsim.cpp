@@ -39,6 +39,16 @@ struct HostExec {
         if (flag != nullptr && *flag == 0u) return;
         launch<Tag>(n, f);
     }
+    template <class Tag, class Pred, class Emit>
+    void select(i64 n, Pred pred, Emit emit, u32* count, AggArena&) {
+        // the predicate of every element is evaluated before any emit runs (on the GPU both happen inside one pass, with
+        // no ordering between different elements): emits must not change what a predicate reads
+        std::vector<char> keep((size_t)(n > 0 ? n : 0));
+        launch<Tag>(n, [&](i64 i) { keep[(size_t)i] = pred(i) ? 1 : 0; });
+        i64 pos = 0;
+        for (i64 i = 0; i < n; i++) if (keep[(size_t)i]) emit(i, pos++);
+        count[0] = (u32)pos;
+    }
     void fill_u32(u32* p, u32 v, i64 n) { for (i64 i = 0; i < n; i++) p[i] = v; }
     void read_u32s(const u32* p, u32* host, int count) { for (int i = 0; i < count; i++) host[i] = p[i]; }
     void exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&, u32* total) {

@@ -227,3 +227,32 @@ def test_io_round_trip_and_plotting_surface(tmp_path, golden):
     vis = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(vis)
     vis.plotOrderedDensity(c2)
+
+
+def test_integration_md_stub_runs_and_matches():
+    """The ctypes stub of INTEGRATION.md section 2 -- the three stage methods a maintainer of the reference would patch in --
+    is extracted from the document and executed as written (only the library path is made absolute, and the final lines that
+    patch the reference class, which is not importable on the GPU box, are replaced by a stand-in object carrying the
+    attributes the reference's constructor sets, astrolink.py:132-176).  Its results must equal AstroLink(P)'s."""
+    import os
+    import re
+    import types
+    from astrolink_b200 import AstroLink, synth, _native as nat
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    stub = [b for b in blocks if "def transform_data(self)" in b]
+    assert len(stub) == 1
+    code = stub[0].split("import astrolink.astrolink as ref")[0]
+    code = code.replace('ctypes.CDLL("libastrolink_b200.so")', f'ctypes.CDLL({nat.lib_path()!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    for P, kw in ((synth.halo6d(20011, seed=3, n_sub=8), {}), (synth.two_gaussians(3000, 2, 7, np.float64), {})):
+        c = AstroLink(P, **kw)
+        c.run()
+        o = types.SimpleNamespace(P=P, adaptive=1, k_den=c.k_den, k_link=c.k_link, weights=None, d_intrinsic=c.d_intrinsic)
+        ns["transform_data"](o)
+        ns["estimate_density_and_kNN"](o)
+        ns["aggregate"](o)
+        assert (o.logRho == c.logRho).all()
+        assert (o.ordering == c.ordering).all() and (o.groups == c.groups).all() and (o.prominences == c.prominences).all()
