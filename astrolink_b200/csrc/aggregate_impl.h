@@ -431,7 +431,11 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 const u32 nx = la[e].x;
                 off++;
                 if (nx == NONE) { uint2_agg z; z.x = NONE; z.y = off; ra[r] = z; return; }
-                if (rflag2[nx]) { uint2_agg z; z.x = rid[nx]; z.y = off; ra[r] = z; return; }
+                // (the ruler test is recomputed from the index instead of read from rflag2: one random sector less per
+                // element; the head, the only ruler the hash does not decide, is nobody's successor)
+                u32 hn = nx * 2654435761u;
+                hn ^= hn >> 15;
+                if ((hn & 31u) == 0u) { uint2_agg z; z.x = rid[nx]; z.y = off; ra[r] = z; return; }
                 e = nx;
             }
         });

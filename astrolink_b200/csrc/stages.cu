@@ -367,6 +367,15 @@ __global__ void __launch_bounds__(ME_BLOCK) make_edges_staged_kernel(const T* __
     if (knn_stride == L) {
         const u32* src = knn + b0 * L;
         for (int e = t; e < rows * L; e += ME_BLOCK) s_knn[e] = src[e];
+    } else if (knn_stride == 8 && L <= 8) {
+        // rows padded to 32 bytes (the un-permute pass of the sharded path writes them so): one thread per row, two 128-bit loads
+        if (t < rows) {
+            const uint4* src = reinterpret_cast<const uint4*>(knn + (b0 + t) * 8);
+            const uint4 a = src[0], b = src[1];
+            const u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int c = 0; c < 8; c++) if (c < L) s_knn[t * L + c] = v[c];
+        }
     } else {
         for (int e = t; e < rows * L; e += ME_BLOCK) s_knn[e] = knn[(b0 + e / L) * knn_stride + e % L];
     }
@@ -497,12 +506,30 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const V* __restrict__
     }
 }
 
+// rows of up to 8 four-byte words into 32-byte destination rows: the whole sector is written (padding words zero), so the
+// scattered stores are full-sector writes instead of partial ones that make the memory system read the sector first
+__global__ void __launch_bounds__(256) scatter_rows8_kernel(const u32* __restrict__ src, const u32* __restrict__ perm, i64 rows, int cols,
+                                                            int src_stride, uint4* __restrict__ dst) {
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
+        const u32 to = perm[r];
+        if (to == 0xffffffffu) continue;
+        const u32* s = src + r * src_stride;
+        u32 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = c < cols ? s[c] : 0u;
+        dst[2 * (i64)to] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[2 * (i64)to + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 extern "C" int al_scatter_rows(const void* src, const uint32_t* perm, int64_t rows, int cols, int src_stride, int dst_stride,
                                int elem_bytes, void* dst, void* stream) {
     AL_REQUIRE(elem_bytes == 4 || elem_bytes == 8, AL_EINVAL, "al_scatter_rows: elem_bytes must be 4 or 8");
     if (rows <= 0) return AL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (elem_bytes == 4)
+    if (elem_bytes == 4 && dst_stride == 8 && cols <= 8 && ((uintptr_t)dst & 31) == 0)
+        scatter_rows8_kernel<<<al_grid(rows, 256), 256, 0, st>>>((const u32*)src, perm, rows, cols, src_stride, (uint4*)dst);
+    else if (elem_bytes == 4)
         scatter_rows_kernel<u32><<<al_grid(rows, 256), 256, 0, st>>>((const u32*)src, perm, rows, cols, src_stride, dst_stride, (u32*)dst);
     else
         scatter_rows_kernel<u64><<<al_grid(rows, 256), 256, 0, st>>>((const u64*)src, perm, rows, cols, src_stride, dst_stride, (u64*)dst);
