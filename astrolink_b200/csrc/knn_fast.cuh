@@ -20,8 +20,8 @@
 //     needy queries are tested per iteration (two independent chains);
 //   * leaves of a wide node are visited nearest box first with one warp reduction
 //     per tile over a per-lane key register;
-//   * heap siblings are adjacent in shared memory, so a sift-down level is one
-//     128-bit load, two 64-bit compares and one store; the root lives in a register;
+//   * a 4-ary heap with the four children of a node adjacent in shared memory (two
+//     128-bit loads per level, two levels for k = 20); the root lives in a register;
 //   * the kernel is latency bound at the occupancy its shared memory allows, so the
 //     per-warp footprint is cut to fit 6 CTAs (24 warps) per SM at d = 6, k = 20:
 //     ONE tile buffer (24 resident warps hide the copy of the next tile better than
@@ -66,8 +66,10 @@ struct Geo {
 // per-warp shared memory (bytes from the warp's base).  Everything except the heap's SIZE is a compile-time function of D, and
 // the heap comes last but one, so every address the hot loops use is the warp's base plus a constant (plus a lane term):
 //   tile | queue [QC][32] u64 | query table [32][RS] f32 | own leaf box [D] (lo, hi) | stack masks [8] | mbarrier |
-//   heap pairs [K/2][32][2] u64 (node h's children in pair h; the root in a register) | spilled need masks [n_levels - 1][32] u32
+//   heap quads [ceil((K-1)/4)][2][32][2] u64 (node h's four children in quad h; the root in a register) | spilled need masks [n_levels - 1][32] u32
 __host__ __device__ static inline int spill_rows(int n_levels) { return n_levels > 1 ? n_levels - 1 : 1; }
+// bytes of the per-warp heap below the root: ceil((k - 1) / 4) quads of 1 KB
+__host__ __device__ static inline unsigned heap_bytes(int k) { return (unsigned)((k + 2) >> 2) * 1024u; }
 template <int D>
 struct Smem {
     typedef Geo<D> G;
@@ -77,12 +79,12 @@ struct Smem {
     static constexpr int STK = QBOX + G::BS * 4;
     static constexpr int BAR = STK + MAX_WIDE_LEVELS * 4;
     static constexpr int HEAP = BAR + 16;
-    static_assert(HEAP % 16 == 0, "heap pairs are read with 128-bit loads");
+    static_assert(HEAP % 16 == 0, "heap quads are read with 128-bit loads");
 };
 template <int D>
 static inline int warp_smem_bytes(int k, int n_levels) {
     size_t b = (size_t)Smem<D>::HEAP;
-    b += (size_t)(k / 2) * 512;
+    b += heap_bytes(k);
     b += (size_t)spill_rows(n_levels) * 128;
     return (int)al_align(b, 16);      // d=6, k=20, 4 levels: 9 312 B -> 6 CTAs of 4 warps per SM
 }
@@ -149,33 +151,45 @@ __device__ __forceinline__ void load_qrow(u32 row_sa, float* r) {
     }
 }
 
-// Replaces the root of a max-heap of `size` nodes by v and restores the heap.  Node 0 is `root` (a register); node h's
-// children 2h + 1 and 2h + 2 are the two halves of pair h, 512 bytes apart per h from pair0_sa.  A right child that does not
-// exist holds key 0 (never "worse"), except in a heap that is being shrunk (SHRUNK: the epilogue's heapsort), where the slot
-// past the end holds an extracted key and is masked here.
+// Replaces the root of a 4-ary max-heap of `size` nodes by v and restores the heap.  Node 0 is `root` (a register).
+// Node h's children 4h + 1 .. 4h + 4 are quad h: two 16-byte halves (children 0-1, children 2-3), each
+// laid out [lane][2] (conflict-free 128-bit loads), a quad every 1024 bytes from quad0_sa (this lane's quad 0, first half).
+// For k = 20 the heap is two levels deep: a replacement costs at most two quads.  Missing children hold key 0.
+__device__ __forceinline__ u32 quad_slot_sa(u32 quad0_sa, u32 quad_off, u32 r) { return quad0_sa + quad_off + (r >> 1) * 512u + (r & 1u) * 8u; }
 template <bool SHRUNK>
-__device__ __forceinline__ void heap_replace(u64& root, u32 pair0_sa, int size, u64 v) {
-    const u32 pa_end = pair0_sa + (u32)(size >> 1) * 512u;      // pairs with a left child below `size`
-    if (pair0_sa >= pa_end) { root = v; return; }
-    u64 c0, c1;
-    lds64x2(pair0_sa, c0, c1);
-    if (SHRUNK && pair0_sa + 512u == pa_end && !(size & 1)) c1 = 0ull;
-    u32 r8 = c1 > c0 ? 8u : 0u;
-    u64 ck = r8 ? c1 : c0;
-    if (!(ck > v)) { root = v; return; }
+__device__ __forceinline__ bool heap4_level(u32 quad0_sa, u32 off, u32 q_end, int size, u64 v, u64& ck, u32& r) {
+    u64 c0, c1, c2, c3;
+    lds64x2(quad0_sa + off, c0, c1);
+    lds64x2(quad0_sa + off + 512u, c2, c3);
+    if (SHRUNK && off + 1024u == q_end) {       // the last quad of a heap that is being shrunk: slots past `size` hold extracted keys
+        const int valid = size - 1 - (int)(off >> 8);
+        if (valid < 2) c1 = 0ull;
+        if (valid < 3) c2 = 0ull;
+        if (valid < 4) c3 = 0ull;
+    }
+    const bool r01 = c1 > c0, r23 = c3 > c2;
+    const u64 m01 = r01 ? c1 : c0, m23 = r23 ? c3 : c2;
+    const bool hi = m23 > m01;
+    ck = hi ? m23 : m01;
+    r = hi ? (r23 ? 3u : 2u) : (r01 ? 1u : 0u);
+    return ck > v;
+}
+template <bool SHRUNK>
+__device__ __forceinline__ void heap4_replace(u64& root, u32 quad0_sa, int size, u64 v) {
+    const u32 q_end = (u32)((size + 2) >> 2) * 1024u;       // quads with a node below `size`
+    if (q_end == 0u) { root = v; return; }
+    u64 ck;
+    u32 r;
+    if (!heap4_level<SHRUNK>(quad0_sa, 0u, q_end, size, v, ck, r)) { root = v; return; }
     root = ck;
-    u32 hole = pair0_sa + r8;
-    u32 pa = pair0_sa + 512u + (r8 << 6);       // node h's worse child is node 2h + 1 + r: offset -> 2 offset + 512 (1 + r)
+    u32 hole = quad_slot_sa(quad0_sa, 0u, r);
+    u32 off = 1024u + r * 1024u;                            // node h's child r is node 4h + 1 + r: offset -> 4 offset + 1024 (1 + r)
 #pragma unroll 1
-    while (pa < pa_end) {
-        lds64x2(pa, c0, c1);
-        if (SHRUNK && pa + 512u == pa_end && !(size & 1)) c1 = 0ull;
-        r8 = c1 > c0 ? 8u : 0u;
-        ck = r8 ? c1 : c0;
-        if (!(ck > v)) break;
+    while (off < q_end) {
+        if (!heap4_level<SHRUNK>(quad0_sa, off, q_end, size, v, ck, r)) break;
         sts64(hole, ck);
-        hole = pa + r8;
-        pa = pair0_sa + 2u * (pa - pair0_sa) + 512u + (r8 << 6);
+        hole = quad_slot_sa(quad0_sa, off, r);
+        off = 4u * off + 1024u + r * 1024u;
     }
     sts64(hole, v);
 }
@@ -191,7 +205,6 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     if (ql64 >= p.leaf_end) return;
     const int ql = (int)ql64;
     const int K = p.k;
-    const int NP = K >> 1;                       // sibling pairs of the heap (node h's children live in pair h)
     const int n_levels = p.n_levels;
 
     // ---- shared addresses: the warp's base plus compile-time offsets (see Smem)
@@ -204,8 +217,8 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     const u32 qbox_sa = tile_sa + S::QBOX;                                 // own leaf's box, (lo_j, hi_j) pairs
     const u32 stk_sa = tile_sa + S::STK;                                   // children masks of the entries below the top
     const u32 bar_sa = tile_sa + S::BAR;                                   // the tile buffer's mbarrier
-    const u32 pair_sa = tile_sa + S::HEAP + (u32)lane * 16u;               // this lane's pair 0 (pair stride 512)
-    const u32 need_sa = tile_sa + S::HEAP + (u32)NP * 512u + (u32)lane * 4u;   // spilled need masks, this lane's column (row stride 128)
+    const u32 quad_sa = tile_sa + S::HEAP + (u32)lane * 16u;               // this lane's quad 0, first half (quad stride 1024)
+    const u32 need_sa = tile_sa + S::HEAP + heap_bytes(K) + (u32)lane * 4u;    // spilled need masks, this lane's column (row stride 128)
     const u32 myrow_sa = qt_sa + (u32)lane * (G::RS * 4u);
 
     const u64 kinf = make_key(INFINITY, 0xffffffffu);
@@ -214,7 +227,10 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #pragma unroll 1
-    for (int h = 0; h < NP; h++) sts64x2(pair_sa + (u32)h * 512u, kinf, (2 * h + 2 < K) ? kinf : 0ull);   // a missing right sibling is never "worse"
+    for (int h = 0; 4 * h + 1 < K; h++) {       // a missing child is never "worse"
+        sts64x2(quad_sa + (u32)h * 1024u, kinf, (4 * h + 2 < K) ? kinf : 0ull);
+        sts64x2(quad_sa + (u32)h * 1024u + 512u, (4 * h + 3 < K) ? kinf : 0ull, (4 * h + 4 < K) ? kinf : 0ull);
+    }
 #pragma unroll
     for (int j = 0; j < G::RS; j++) stsf(myrow_sa + 4u * j, j == D ? -1.f : 0.f);
     if (lane < G::BS) stsf(qbox_sa + 4u * lane, ((const float*)p.box[0])[(size_t)ql * G::BS + lane]);
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
         for (int t = 0; t < maxc; t++) {
             const u64 v = lds64(queue_sa + (u32)t * 256u);      // slots past cnt hold stale keys: masked by the test below
             if (t < cnt && root > v) {
-                heap_replace<false>(root, pair_sa, K, v);
+                heap4_replace<false>(root, quad_sa, K, v);
                 if (KNN_STATS) st_insert++;
             }
             if (KNN_STATS) st_rounds++;
@@ -545,13 +561,14 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
 
     // ---- heap -> ascending order in place (heapsort over the paired layout; node 0 ends up in queue slot 0), then the outputs
     auto node_sa = [&](int m, int r) -> u32 {       // heap node m of lane r
-        return m == 0 ? queue_sa + (u32)(r - lane) * 8u : pair_sa + (u32)(r - lane) * 16u + (u32)((m - 1) >> 1) * 512u + (u32)((m - 1) & 1) * 8u;
+        if (m == 0) return queue_sa + (u32)(r - lane) * 8u;
+        return quad_slot_sa(quad_sa + (u32)(r - lane) * 16u, (u32)((m - 1) >> 2) * 1024u, (u32)((m - 1) & 3));
     };
 #pragma unroll 1
     for (int m = K - 1; m >= 1; m--) {
         const u64 v = lds64(node_sa(m, lane));
         sts64(node_sa(m, lane), root);      // the largest of the m + 1 remaining keys
-        heap_replace<true>(root, pair_sa, m, v);
+        heap4_replace<true>(root, quad_sa, m, v);
     }
     sts64(queue_sa, root);
     const bool active = my_id != 0xffffffffu;

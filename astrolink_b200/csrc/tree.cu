@@ -240,7 +240,10 @@ __global__ void tree_split_kernel(u32* nodeA, u32* nodeB, i64 n_leaves, int leve
 // ---------------------------------------------------------------------------
 constexpr int BOT_LEAVES = 128;
 constexpr int BOT_POINTS = BOT_LEAVES * LEAF;     // 4096
-constexpr int BOT_THREADS = 512;
+#ifndef AL_BOT_THREADS
+#define AL_BOT_THREADS 512
+#endif
+constexpr int BOT_THREADS = AL_BOT_THREADS;
 constexpr int BOT_ITEMS = BOT_POINTS / BOT_THREADS;
 #ifndef AL_BOT_RADIX_BITS
 #define AL_BOT_RADIX_BITS 4

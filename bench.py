@@ -13,13 +13,24 @@ and N>1 shards its queries: strong scaling).  Metric: points/sec.
           D2H of logRho / ordering / groups / prominences inside the timed region
   roofline     : the kNN kernel (dominant kernel), FP32 pipe: 3*d flop per evaluated
                  (query, candidate) pair, pairs counted by the kernel, duration by CUDA
-                 events on the launching stream; peak = FP32 FMA rate measured in-run
-  cpu_baseline : the CPU oracle port of the same path timed on this box's host cores
-                 on a bounded sample of the workload (rank 0, N=1 only)
+                 events on the launching stream; peak = FP32 FMA rate measured in-run;
+                 traffic = DRAM bytes of this round's `ncu --set full` capture
+  hbm_passes   : algorithmic bytes, ms and GB/s of every other stage (rescale, index build,
+                 normalise, edges, sort, aggregation; the density pass is fused into the
+                 search epilogue and its stand-alone kernel is timed once for the record)
+  result_checksum : digest of ordering / groups / clusters / logRho -- equal at every N
+  cpu_baseline : the CPU oracle port of the same path timed on this box's host cores on a
+                 FIXED 2M-point prefix of the workload (rank 0, N=1 only), with the
+                 committed full-size timings next to it (full_config_extrapolation)
+
+Multi-GPU (N > 1): the searching ranks run ahead of rank 0 by at most one run (rank 0 does
+the globally ordered tail), so consecutive steps pipeline; the first step of the timed series
+pays the un-overlapped tail once.  Time is the max over ranks of CUDA-event time.
 
 Timing: W >= 3 warm-up steps, K timed steps bracketed by barrier + synchronize,
-CUDA events, max over ranks.  The working set (P 240 MB, neighbour lists 1.6 GB,
-60M edges) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+CUDA events, max over ranks.  The working set (P 240 MB, index 280 MB, 60M edges 720 MB)
+is far larger than the 126 MB L2 and every step allocates fresh buffers: no explicit L2
+flush is needed (config.l2 lists the sizes of the workload actually run).
 """
 import argparse
 import json
