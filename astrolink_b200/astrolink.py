@@ -497,7 +497,7 @@ class AstroLink:
         start = time.perf_counter()
         self._finish_fetch(("groups", "prominences"))
         prom = self.prominences
-        if prom.shape[0] >= 16384:
+        if prom.shape[0] >= 512:
             # large group counts: the O(G) objective is evaluated on the GPU, SciPy still drives the fit
             with torch.cuda.device(self._device):
                 obj = nat.W1Objective(self._dev("prominences"))

@@ -23,11 +23,16 @@ DEAL_CHUNK_LEAVES = 1024     # leaves per dealt chunk (32 768 points): small eno
                              # large enough that a chunk's candidate tiles stay hot in L2
 
 
-def tail_aware_widths(world):
+TAIL_OVER_SEARCH = 0.24      # rank 0's tail (un-permute .. host statistics) relative to the whole search, measured on C4 / one B200
+
+
+def tail_aware_widths(world, tail_over_search=TAIL_OVER_SEARCH):
     """Shares of the search the ranks take, in dealt chunks per round of the deal.  Rank 0 also runs everything after the
-    exchange (edges, sort, aggregation, host statistics -- the globally ordered part, north-star item 4), about a quarter of
-    the single-GPU step, so it takes less of the search: 3 of 8 chunks on two GPUs, none from three GPUs up -- a dedicated
-    tail rank, so that run i's tail overlaps run i + 1's search on the other ranks (the peer buffers are double-buffered).
+    exchange (edges, sort, aggregation, host statistics -- the globally ordered part, north-star item 4), so it takes less
+    of the search: the share s that equalises `index + s search + tail` on rank 0 with `index + (1 - s) search / (N - 1)`
+    on the others, s = (1 - t (N - 1)) / N with t = tail / search -- 3 of 8 chunks on two GPUs, 2 of 12 on three, 1 of 13
+    on four, and none from five GPUs up: a dedicated tail rank that builds no index either.  The peer buffers are
+    double-buffered, so run i's tail overlaps run i + 1's search on the other ranks.
     AL_TAIL_WIDTHS="w0,w1,..." overrides (development)."""
     import os
     env = os.environ.get("AL_TAIL_WIDTHS")
@@ -37,9 +42,19 @@ def tail_aware_widths(world):
         return w
     if world == 1:
         return [1]
-    if world == 2:
-        return [3, 5]
-    return [0] + [1] * (world - 1)
+    s = (1.0 - tail_over_search * (world - 1)) / world
+    if s <= 0.02:
+        return [0] + [1] * (world - 1)
+    # smallest integer widths (w0, wk, ..., wk) whose share w0 / (w0 + (N - 1) wk) is within 4 % of s
+    best = None
+    for wk in range(1, 9):
+        w0 = max(1, round(s * (world - 1) * wk / (1.0 - s)))
+        err = abs(w0 / (w0 + (world - 1) * wk) - s) / s
+        if best is None or err < best[0] - 1e-9:
+            best = (err, w0, wk)
+        if err <= 0.04:
+            break
+    return [best[1]] + [best[2]] * (world - 1)
 
 
 def deal_chunks(positions, rank, world, leaf=32, chunk_leaves=DEAL_CHUNK_LEAVES, widths=None):

@@ -217,8 +217,12 @@ def run_reference(args):
     oracle.build()
     oracle.set_num_threads()          # all host cores, even under torchrun (which exports OMP_NUM_THREADS=1)
     P, kwargs, desc = make_workload(args.workload)
+    # The per-step sample is a fixed prefix of the shuffled cloud whose size depends on K only (never on the box or on a
+    # warm-up rate): 2M points up to 5 steps, 10M / K beyond, so that K steps stay within a few minutes of CPU time.
     n_s = min(args.cpu_sample, P.shape[0])
-    # one warm-up on a small prefix (pages the library in); the timed sample is the same fixed prefix on every box
+    if args.steps > 5:
+        n_s = max(250000, min(n_s, 10_000_000 // args.steps))
+    # one warm-up on a small prefix (pages the library in)
     cpu_hot_path_seconds(np.ascontiguousarray(P[:20000]), kwargs)
     sample = np.ascontiguousarray(P[:n_s])          # the cloud is shuffled: a prefix is a uniform sample
     times = []

@@ -100,7 +100,11 @@ def test_weighted_deal_covers_every_position_once():
     the globally ordered tail, fewer or none -- and the positions are still covered exactly once."""
     from astrolink_b200 import dist as adist
     assert adist.tail_aware_widths(1) == [1] and adist.tail_aware_widths(2) == [3, 5]
-    assert adist.tail_aware_widths(4) == [0, 1, 1, 1] and adist.tail_aware_widths(8) == [0] + [1] * 7
+    assert adist.tail_aware_widths(3) == [2, 5, 5] and adist.tail_aware_widths(4) == [1, 4, 4, 4]
+    assert adist.tail_aware_widths(5) == [0, 1, 1, 1, 1] and adist.tail_aware_widths(8) == [0] + [1] * 7
+    for world in range(2, 9):      # rank 0 never takes more than an equal share
+        w = adist.tail_aware_widths(world)
+        assert len(w) == world and w[0] <= w[1] and len(set(w[1:])) == 1
     for positions in (4000 // 32 * 32 + 32, 150016, 10_000_000 // 32 * 32 + 32):
         for widths in ([3, 5], [0, 1, 1, 1], [0, 1, 1], [2, 0, 1], [0] + [1] * 7, [1, 4, 4, 4]):
             world = len(widths)

@@ -51,7 +51,7 @@ td.destroy_process_group()
 
 # The same sharded code on ONE GPU: `world` processes share cuda:0 (gloo process group for the barrier and the handle
 # broadcast; the peer buffers are CUDA IPC mappings of rank 0's memory, here on the same device).  world 2: rank 0 takes
-# 3 of 8 chunks; world 3: rank 0 is a dedicated tail rank and gets the index permutation from rank 1.
+# 3 of 8 chunks; world 3: 2 of 12, or -- AL_TAIL_WIDTHS=0,1,1 -- none: a dedicated tail rank that gets the index permutation from rank 1.
 SCRIPT_ONE_GPU = r'''
 import os, sys
 sys.path.insert(0, os.environ["AL_ROOT"])
@@ -98,14 +98,18 @@ def test_sharded_run_equals_single_gpu(tmp_path):
     assert "MULTI_OK" in r.stdout
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_run_on_one_gpu_equals_single_process(tmp_path, world):
-    """The sharded path without a second GPU: `world` processes on cuda:0 (see SCRIPT_ONE_GPU)."""
+@pytest.mark.parametrize("world,widths", [(2, None), (3, None), (3, "0,1,1")])
+def test_sharded_run_on_one_gpu_equals_single_process(tmp_path, world, widths):
+    """The sharded path without a second GPU: `world` processes on cuda:0 (see SCRIPT_ONE_GPU).  widths None: the default
+    tail-aware deal (rank 0 searches a smaller share); "0,1,1": rank 0 as a dedicated tail rank (the deal from five GPUs
+    up), which builds no index and receives the index permutation from rank 1."""
     script = tmp_path / "multi1.py"
     script.write_text(SCRIPT_ONE_GPU)
     env = dict(os.environ, AL_ROOT=ROOT, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    if widths is not None:
+        env["AL_TAIL_WIDTHS"] = widths
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", str(29741 + world), str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(29741 + world + (10 if widths else 0)), str(script)],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_OK" in r.stdout
