@@ -24,5 +24,7 @@ for tag in tags:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); d2, idx = index.knn(20); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    print(f"{tag:6s} knn {best:8.3f} ms  checksum idx {int(idx.to(torch.int64).sum().item())} d2 {float(d2.double().sum().item()):.9e}", flush=True)
+    _, _, pairs = index.knn(20, count_pairs=True)
+    pairs = int(pairs[0].item())
+    print(f"{tag:6s} knn {best:8.3f} ms  tiles/query {pairs / 32 / n:6.1f}  checksum idx {int(idx.to(torch.int64).sum().item())} d2 {float(d2.double().sum().item()):.9e}", flush=True)
     del index, d2, idx
