@@ -18,8 +18,16 @@
 //     128-bit-aligned row per node: a lane reads its child's box with 128-bit loads,
 //     a per-axis gap is one FADD2 (q - lo, q - hi), one 3-input max, one FFMA, and two
 //     needy queries are tested per iteration (two independent chains);
-//   * leaves of a wide node are visited nearest box first with one warp reduction
-//     per tile over a per-lane key register;
+//   * the children of a node -- leaves and wide nodes alike -- are visited in the order
+//     of a per-lane key register, one warp reduction per pick: the child most queries
+//     need first, then the nearest box (the k-th distances tighten early; 16 bits of
+//     the keys of an interrupted wide node are spilled with its need masks);
+//   * the tile copy is issued by an elected lane and the warp's shared base is a
+//     uniform register the compiler knows about (a `lane == 0` test around the
+//     uniform-operand copy costs a divergence-proof broadcast loop per tile); the
+//     lane number is opaque so that it is not rematerialised from %tid in the loops;
+//   * the sparse passes locate the next pass's query rows under the loads of the
+//     current one (the bit-scan chain and the FMA chain overlap);
 //   * a 4-ary heap with the four children of a node adjacent in shared memory (two
 //     128-bit loads per level, two levels for k = 20); the root lives in a register;
 //   * the kernel is latency bound at the occupancy its shared memory allows, so the
@@ -41,24 +49,6 @@
 #endif
 #ifndef KF_OPEN2
 #define KF_OPEN2 1             // box tests: two needy queries per iteration (two independent chains)
-#endif
-#ifndef KF_WIDE_NEAREST
-#define KF_WIDE_NEAREST 1      // 1: the children of wide nodes are visited nearest box first too (leaf lists always are)
-#endif
-#ifndef KF_RETEST
-#define KF_RETEST 0            // 1: every query re-tests a fetched tile's box against its CURRENT k-th distance (need masks age)
-#endif
-#ifndef KF_ORDER
-#define KF_ORDER 3             // visiting order of a node's children: 0 box distance to the own leaf; 1 centre distance; 2 box, then centre;
-#endif                         // 3 most needed first, then box distance; 4 box distance, then most needed
-#ifndef KF_ELECT
-#define KF_ELECT 1             // tile copy issued by: 0 lane 0, 1 an elected lane, 2 an elected lane with the leaf number re-uniformised
-#endif
-#ifndef KF_UBASE
-#define KF_UBASE 1             // 1: the warp's shared base is warp-uniform to the compiler (a uniform register) instead of opaque
-#endif
-#ifndef KF_LANE_OPAQUE
-#define KF_LANE_OPAQUE 1       // 1: the lane number cannot be rematerialised from %tid (S2R in the loops)
 #endif
 #ifndef KF_MINBLOCKS
 #define KF_MINBLOCKS 6         // CTAs per SM the register allocation is held to for d <= 8 (80 registers)
@@ -97,7 +87,7 @@ struct Smem {
     static constexpr int STK = QBOX + G::BS * 4;
     static constexpr int BAR = STK + MAX_WIDE_LEVELS * 4;
     static constexpr int KEYS = BAR + 16;                      // 16-bit visiting-order keys of the spilled level-2 and level-3 entries, [2][32]
-    static constexpr int HEAP = KEYS + (KF_WIDE_NEAREST ? 128 : 0);
+    static constexpr int HEAP = KEYS + 128;
     static_assert(HEAP % 16 == 0, "heap quads are read with 128-bit loads");
 };
 template <int D>
@@ -234,13 +224,9 @@ template <int D>
 __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(const KnnParams p) {
     typedef Geo<D> G;
     extern __shared__ __align__(128) unsigned char smem[];
-#if KF_LANE_OPAQUE
     int lane;
     asm volatile("and.b32 %0, %1, 31;" : "=r"(lane) : "r"(threadIdx.x));
     const int wib = threadIdx.x >> 5;
-#else
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-#endif
     i64 gblock = blockIdx.x;
     if (p.chunk_blocks > 0) gblock = (gblock / p.chunk_blocks) * p.chunk_stride_blocks + gblock % p.chunk_blocks;
     const i64 ql64 = p.leaf_begin + gblock * WARPS + wib;
@@ -252,12 +238,9 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     // ---- shared addresses: the warp's base plus compile-time offsets (see Smem)
     typedef Smem<D> S;
     u32 tile_sa;                                                           // the tile buffer = the warp's base
-    // (opaque to the compiler: held in one register instead of being re-derived from %tid and the shared window in the loops)
-#if KF_UBASE
+    // (warp-uniform by construction -- a shuffle from lane 0 -- so it lives in a uniform register: addresses are base + constant
+    // (+ lane term), and the bulk copy gets its shared operands without a broadcast)
     tile_sa = smem_u32(smem) + (u32)__shfl_sync(FULL, wib, 0) * (u32)p.warp_smem;      // warp-uniform, and the compiler knows
-#else
-    asm volatile("mov.u32 %0, %1;" : "=r"(tile_sa) : "r"(smem_u32(smem) + (u32)wib * (u32)p.warp_smem));
-#endif
     const u32 queue_sa = tile_sa + S::QUEUE + (u32)lane * 8u;              // this lane's queue slot 0 (slot stride 256)
     const u32 qt_sa = tile_sa + S::QT;                                     // query table
     const u32 qbox_sa = tile_sa + S::QBOX;                                 // own leaf's box, (lo_j, hi_j) pairs
@@ -326,7 +309,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
             if (2 * v < D) bx[2 * v] = pack2(f.x, f.y);
             if (2 * v + 1 < D) bx[2 * v + 1] = pack2(f.z, f.w);
         }
-        float acc = 0.f, cdist = 0.f;
+        float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < D; j++) {
             float lo, hi, qlo, qhi;
@@ -334,10 +317,6 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
             ldsf2(qbox_sa + 8u * j, qlo, qhi);
             const float g = fmaxf(fmaxf(lo - qhi, qlo - hi), 0.f);
             acc = __fmaf_rn(g, g, acc);
-#if KF_ORDER == 1 || KF_ORDER == 2
-            const float cj = (lo + hi) - (qlo + qhi);
-            cdist = __fmaf_rn(cj, cj, cdist);
-#endif
         }
         const bool pass = ok && acc <= bound;
         u32 mask = 0;
@@ -388,17 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
         }
         cmask = mask;
         // order only: a few bits of distance are plenty
-#if KF_ORDER == 1
-        const u32 ord = __float_as_uint(cdist) & ~31u;
-#elif KF_ORDER == 2
-        const u32 ord = (__float_as_uint(acc) & 0xffff0000u) | ((__float_as_uint(cdist) >> 16) & 0xffe0u);
-#elif KF_ORDER == 3
         const u32 ord = ((u32)(32 - __popc(mask)) << 27) | ((__float_as_uint(acc) >> 5) & 0x07ffffe0u);
-#elif KF_ORDER == 4
-        const u32 ord = (__float_as_uint(acc) & 0xffff0000u) | ((u32)(32 - __popc(mask)) << 11);
-#else
-        const u32 ord = __float_as_uint(acc) & ~31u;
-#endif
         okey = mask != 0 ? (ord | (u32)lane) : 0xffffffffu;
         return __ballot_sync(FULL, mask != 0);
     };
@@ -442,23 +411,16 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
                     cmask = lds32(need_sa + (u32)(sp - 1) * 128u);
                     t_node >>= 5;
                     t_h++;
-#if KF_WIDE_NEAREST
                     // the entry's order keys: 16 bits of box distance for levels 2 and 3 (index order above)
                     const u32 k16 = t_h <= 3 ? lds16(keys_sa + (u32)(t_h - 2) * 64u) : 0u;
                     okey = ((t_mask >> lane) & 1u) ? ((k16 << 16) | (u32)lane) : 0xffffffffu;
-#endif
                 }
                 continue;
             }
-#if KF_WIDE_NEAREST
             const int bit = (int)(__reduce_min_sync(FULL, okey) & 31u);
             t_mask &= ~(1u << bit);
             if (lane == bit) okey = 0xffffffffu;
             if (t_h <= 3) sts16(keys_sa + (u32)(t_h - 2) * 64u, okey >> 16);
-#else
-            const int bit = __ffs(t_mask) - 1;
-            t_mask &= t_mask - 1;
-#endif
             const u32 need = __shfl_sync(FULL, cmask, bit);
             const int c = t_node * FANOUT + bit;
             // descend: spill the top entry, open the children of node c (a level t_h-1 node) for the queries that need it
@@ -475,24 +437,13 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
 
     // Tile number t of this warp completes phase t & 1 of the buffer's barrier.
     auto issue_tile = [&](int leaf) {
-#if KF_ELECT
         // (an elected lane instead of `lane == 0`: the copy takes uniform-register operands, and a lane test costs a
         // divergence-proof broadcast loop around it)
-#if KF_ELECT == 2
-        const u32 uleaf = __reduce_min_sync(FULL, (u32)leaf);
-#else
         const u32 uleaf = (u32)leaf;
-#endif
         if (elect_one()) {
             mbar_expect_tx_sa(bar_sa, (u32)G::TS);
             tma_load_1d_sa(tile_sa, p.tiles + (size_t)uleaf * (u32)G::TS, (u32)G::TS, bar_sa);
         }
-#else
-        if (lane == 0) {
-            mbar_expect_tx_sa(bar_sa, (u32)G::TS);
-            tma_load_1d_sa(tile_sa, p.tiles + (size_t)(u32)leaf * (u32)G::TS, (u32)G::TS, bar_sa);
-        }
-#endif
         if (KNN_STATS) st_loaded++;
     };
     auto wait_tile = [&](u32 t) {
@@ -564,15 +515,21 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     auto eval_sparse = [&](const u64* cand, u32 id0, u32 id1, u32 need) {
         n_qt += __popc(need);
         u32 m = need;
+        u32 ba = m & (0u - m);
+        m ^= ba;
+        u32 bb = m & (0u - m);
+        m ^= bb;
+        u32 row_sa = qt_sa + (u32)((31 - __clz((lane < 16 || bb == 0u) ? ba : bb)) * (G::RS * 4));
 #pragma unroll 1
-        while (m) {
-            const u32 ba = m & (0u - m);
-            m ^= ba;
-            const u32 bb = m & (0u - m);
-            m ^= bb;
-            const int myq = 31 - __clz((lane < 16 || bb == 0u) ? ba : bb);
+        for (;; ) {
             float row[G::RS];
-            load_qrow<D>(qt_sa + (u32)(myq * (G::RS * 4)), row);
+            load_qrow<D>(row_sa, row);
+            // the next pass's pair of queries and their rows: an integer chain that runs under the loads
+            const u32 nba = m & (0u - m);
+            m ^= nba;
+            const u32 nbb = m & (0u - m);
+            m ^= nbb;
+            const u32 nrow_sa = qt_sa + (u32)((31 - __clz((lane < 16 || nbb == 0u) ? nba : nbb)) * (G::RS * 4));
             u64 acc = 0ull;
 #pragma unroll
             for (int j = 0; j < D; j++) {
@@ -591,6 +548,10 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
                 emit(b0 >> 16, d0, id0, qb, 16);
                 emit(b1 >> 16, d1, id1, qb, 16);
             }
+            if (nba == 0u) break;
+            ba = nba;
+            bb = nbb;
+            row_sa = nrow_sa;
         }
     };
 
@@ -618,36 +579,16 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     if (first >= 0) {
         u32 cur_need = cand_need;
         u32 t = 1;
-        int cur_leaf = first;
         __syncwarp();       // every lane is done reading the own leaf
         issue_tile(first);
 #pragma unroll 1
         for (;;) {
             const int nxt = next_candidate();
             const u32 nxt_need = cand_need;
-#if KF_RETEST
-            {
-                const float4* brow = reinterpret_cast<const float4*>((const float*)p.box[0] + (size_t)cur_leaf * G::BS);
-                float pd = 0.f;
-#pragma unroll
-                for (int v = 0; v < G::PB4; v++) {
-                    const float4 f = __ldg(brow + v);
-                    if (2 * v < D) {
-                        const float g = fmaxf(fmaxf(f.x - q[2 * v], q[2 * v] - f.y), 0.f);
-                        pd = __fmaf_rn(g, g, pd);
-                    }
-                    if (2 * v + 1 < D) {
-                        const float g = fmaxf(fmaxf(f.z - q[2 * v + 1], q[2 * v + 1] - f.w), 0.f);
-                        pd = __fmaf_rn(g, g, pd);
-                    }
-                }
-                cur_need &= __ballot_sync(FULL, pd <= worst);
-            }
-#endif
             wait_tile(t);
             if (KNN_BRUTE || __popc(cur_need) > KF_SPARSE_MAX) {
                 eval_dense();
-            } else if (!KF_RETEST || cur_need != 0u) {
+            } else {
                 u64 cand[D + 1];
 #pragma unroll
                 for (int v4 = 0; v4 < G::PB4; v4++) {
@@ -663,7 +604,6 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
             __syncwarp();       // every lane is done with the tile (its loads have been consumed)
             issue_tile(nxt);
             cur_need = nxt_need;
-            cur_leaf = nxt;
             t++;
         }
     }
