@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     int cnt = 0;                // queue fill
     u32 my_id = 0xffffffffu;
     u32 n_qt = 0;               // (query, tile) evaluations
+    u32 st_n[3] = {0, 0, 0};            // (KNN_STATS == 2) evaluated tiles needed by 1, 2, 3-4 queries
+    u32 st_lvl[4] = {0, 0, 0, 0};       // (KNN_STATS == 2) needy queries of the evaluated tiles, by ancestor level
     u32 st_loaded = 0, st_dense = 0, st_push = 0, st_insert = 0, st_rounds = 0, st_open_iter = 0, st_descents = 0;
 
     auto flush = [&]() {
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
         __syncwarp();
         bound = warp_max_t<float>(worst);
     };
+
 
     // Open a wide node: lane j takes child j (a level-`hc` node), box-to-box test against the warp bound, then for every
     // query in `qmask` the distance from the query to the child's box against the query's own k-th distance.  The child's
@@ -579,13 +582,22 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
     if (first >= 0) {
         u32 cur_need = cand_need;
         u32 t = 1;
+        int cur_lvl = anc - 2;
         __syncwarp();       // every lane is done reading the own leaf
         issue_tile(first);
 #pragma unroll 1
         for (;;) {
             const int nxt = next_candidate();
             const u32 nxt_need = cand_need;
+            const int nxt_lvl = anc - 2;        // (diagnostics) the ancestor the candidate was found under: 0 = the parent
             wait_tile(t);
+            if (KNN_STATS == 2) {
+                st_lvl[cur_lvl < 4 ? cur_lvl : 3] += __popc(cur_need);
+                const int nn = __popc(cur_need);
+                if (nn == 1) st_n[0]++;
+                else if (nn == 2) st_n[1]++;
+                else if (nn <= 4) st_n[2]++;
+            }
             if (KNN_BRUTE || __popc(cur_need) > KF_SPARSE_MAX) {
                 eval_dense();
             } else {
@@ -604,6 +616,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
             __syncwarp();       // every lane is done with the tile (its loads have been consumed)
             issue_tile(nxt);
             cur_need = nxt_need;
+            if (KNN_STATS == 2) cur_lvl = nxt_lvl;
             t++;
         }
     }
@@ -671,7 +684,10 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
         // [0] (query, candidate) pairs evaluated; the rest are diagnostics (only maintained in KNN_STATS builds)
         if (lane == 0) {
             atomicAdd(p.stats + 0, (unsigned long long)n_qt * LEAF);
-            if (KNN_STATS) {
+            if (KNN_STATS == 2) {
+                for (int l = 0; l < 4; l++) atomicAdd(p.stats + 1 + l, (unsigned long long)st_lvl[l]);
+                for (int l = 0; l < 3; l++) atomicAdd(p.stats + 5 + l, (unsigned long long)st_n[l]);
+            } else if (KNN_STATS) {
                 atomicAdd(p.stats + 1, (unsigned long long)st_loaded);          // tiles fetched
                 atomicAdd(p.stats + 2, (unsigned long long)st_dense);           // of which evaluated densely
                 atomicAdd(p.stats + 3, (unsigned long long)st_descents);        // wide nodes opened below the ancestors
@@ -679,7 +695,7 @@ __global__ void __launch_bounds__(WARPS * 32, Geo<D>::MINB) knn_fast_kernel(cons
                 atomicAdd(p.stats + 7, (unsigned long long)st_open_iter);       // iterations of the box-test loop
             }
         }
-        if (KNN_STATS) {
+        if (KNN_STATS == 1) {
             const u32 pushes = __reduce_add_sync(FULL, st_push), inserts = __reduce_add_sync(FULL, st_insert);
             if (lane == 0) {
                 atomicAdd(p.stats + 4, (unsigned long long)pushes);
