@@ -384,7 +384,7 @@ def run_b200(args):
         "index_build": n * d * esz + (n // 32) * ((tile_bytes + 127) // 128 * 128) + n * 4,   # read P once, write tiles + permutation
         "normalise": 3 * n * esz,
         "edges": n * L * 4 + n * L * esz + n * esz + E * (esz + 8),
-        "sort": E * 4 + E * 68 + E * 16,
+        "sort": E * esz + esz * 2 * E * (esz + 8),     # histogram pass over the keys + one one-sweep pass per key byte reading and writing (key, 64-bit pair)
         "aggregate": E * 8 + n * esz + n * 4 + n_groups * (12 + 2 * esz),     # read the sorted pairs and logRho once, write ordering + rows
     }
     stages_out = {k: round(v, 3) for k, v in stage.items()}

@@ -159,7 +159,9 @@ int al_make_edges(const void* logrho, int dtype, const uint32_t* knn, int64_t kn
 /* ---- a9: pairs[edges.argsort()[::-1]] (astrolink.py:341) ----------------
  * Canonical total order: weight descending, slot ascending (the reference's
  * argsort is unstable).  Stable descending radix sort (CUB).
- * order_out (uint32[E], may be NULL) receives the sorted slot indices. */
+ * order_out (uint32[E], may be NULL) receives the sorted slot indices; without
+ * it the pairs travel through the sort as 64-bit values (no slot numbers, no
+ * gather).  pairs and sorted_pairs_out must be 8-byte aligned. */
 size_t al_sort_edges_workspace_bytes(int dtype, int64_t E);
 int al_sort_edges(const void* weights, int dtype, const uint32_t* pairs, int64_t E,
                   uint32_t* sorted_pairs_out, uint32_t* order_out, void* ws, size_t ws_bytes, void* stream);

@@ -80,6 +80,8 @@ def test_edges_and_order_bit_exact(name, golden):
     sp, order = nat.sort_edges(w, pairs, want_order=True)
     assert (nat.u32_numpy(order).astype(np.int64) == g["order"]).all(), "canonical order: weight desc, slot asc"
     assert (nat.u32_numpy(sp) == g["pairs"][g["order"]]).all()
+    # without the slot order the pairs ride through the sort as 64-bit values: the same stable order, the same bytes
+    assert (nat.u32_numpy(nat.sort_edges(w, pairs)) == g["pairs"][g["order"]]).all()
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names()])
