@@ -160,6 +160,143 @@ __global__ void __launch_bounds__(256) tree_node_bounds_kernel(const T* __restri
     flush();
 }
 
+// After a round's sort: the point rows and ids follow the new order into the other buffer -- so every later pass of the
+// build reads them sequentially, and this gather is local to the node that was sorted -- and, in the same pass, the tight
+// boxes of the nodes of the NEXT round are accumulated (the rows are in registers).  Work decomposition as in
+// tree_node_bounds_kernel: a warp per BOUNDS_CHUNK leaves, lane = point of a leaf.
+// V8: rows are a whole number of 8-byte units; the gather takes 64-bit loads (it is bound by sector requests, one per load
+// and lane), NF leaves are in flight per step (the pass is latency bound: slot -> row is a dependent pair of loads), and
+// the leaves' rows -- contiguous in the destination -- leave through shared memory as full-sector stores.  MD bounds d.
+template <typename T, bool V8, int MD, int NF>
+__global__ void __launch_bounds__(256) tree_permute_bounds_kernel(const T* __restrict__ Psrc, const u32* __restrict__ ids_src,
+                                                                  const u32* __restrict__ slots, T* __restrict__ Pdst,
+                                                                  u32* __restrict__ ids_dst, const u32* __restrict__ nodeA,
+                                                                  const u32* __restrict__ nodeB, u32* bbox_lo, u32* bbox_hi, i64 n,
+                                                                  i64 n_leaves, int d, int want_bounds) {
+    constexpr int EPU = 8 / (int)sizeof(T);         // elements per 8-byte unit
+    constexpr int MU = MD / EPU;                     // units per row, at most
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ uint2 stage[V8 ? 256 / 32 : 1][V8 ? NF * LEAF * MU : 1];
+    const i64 leaf0 = ((i64)blockIdx.x * (256 / 32) + wib) * BOUNDS_CHUNK;
+    if (leaf0 >= n_leaves) return;
+    float mn[MD], mx[MD];
+#pragma unroll
+    for (int j = 0; j < MD; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    i64 cur = -1;
+    auto flush = [&]() {
+        if (cur < 0) return;
+#pragma unroll
+        for (int j = 0; j < MD; j++) {
+            if (j < d) {
+                float a = mn[j], b = mx[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+                    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                }
+                if (lane == 0) {
+                    atomicMin(&bbox_lo[cur * d + j], f32_to_ordered(a));
+                    atomicMax(&bbox_hi[cur * d + j], f32_to_ordered(b));
+                }
+            }
+        }
+    };
+    // enters a leaf's node: true if its box is being accumulated
+    auto enter = [&](i64 leaf) -> bool {
+        const u32 a = nodeA[leaf];
+        const bool active = want_bounds && nodeB[leaf] - a > 1;
+        if (active && (i64)a != cur) {
+            flush();
+            cur = a;
+#pragma unroll
+            for (int j = 0; j < MD; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+        }
+        return active;
+    };
+    if (V8) {
+        const int U = d / EPU;                       // units per row
+        uint2* st = stage[wib];
+        for (int c = 0; c < BOUNDS_CHUNK; c += NF) {
+            const i64 leaf = leaf0 + c;
+            if (leaf >= n_leaves) break;
+            bool valid[NF];
+            u32 sl[NF];
+            uint2 r[NF][MU];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const i64 pf = (leaf + f) * LEAF + lane;
+                valid[f] = leaf + f < n_leaves && pf < n;
+                sl[f] = valid[f] ? slots[pf] : 0u;
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const uint2* row = reinterpret_cast<const uint2*>(Psrc + (i64)sl[f] * d);
+#pragma unroll
+                for (int u = 0; u < MU; u++)
+                    if (u < U) r[f][u] = valid[f] ? __ldg(row + u) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                if (valid[f]) ids_dst[(leaf + f) * LEAF + lane] = ids_src[sl[f]];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                if (leaf + f < n_leaves && enter(leaf + f)) {
+#pragma unroll
+                    for (int u = 0; u < MU; u++)
+                        if (u < U && valid[f]) {
+                            if (sizeof(T) == 4) {
+                                const float v0 = __uint_as_float(r[f][u].x), v1 = __uint_as_float(r[f][u].y);
+                                mn[2 * u] = fminf(mn[2 * u], v0);
+                                mx[2 * u] = fmaxf(mx[2 * u], v0);
+                                mn[(2 * u + 1) % MD] = fminf(mn[(2 * u + 1) % MD], v1);
+                                mx[(2 * u + 1) % MD] = fmaxf(mx[(2 * u + 1) % MD], v1);
+                            } else {
+                                const float v0 = (float)__longlong_as_double((long long)(((unsigned long long)r[f][u].y << 32) | r[f][u].x));
+                                mn[u] = fminf(mn[u], v0);
+                                mx[u] = fmaxf(mx[u], v0);
+                            }
+                        }
+                }
+#pragma unroll
+                for (int u = 0; u < MU; u++)
+                    if (u < U) st[(f * LEAF + lane) * U + u] = r[f][u];
+            }
+            __syncwarp();
+            i64 rows_here = n - leaf * LEAF;
+            i64 cap = (n_leaves - leaf) * LEAF;
+            cap = cap < (i64)NF * LEAF ? cap : (i64)NF * LEAF;
+            rows_here = rows_here < cap ? rows_here : cap;
+            uint2* out = reinterpret_cast<uint2*>(Pdst + leaf * LEAF * d);
+            for (int k = lane; k < (int)rows_here * U; k += 32) out[k] = st[k];
+            __syncwarp();
+        }
+    } else {
+        for (int c = 0; c < BOUNDS_CHUNK; c++) {
+            const i64 leaf = leaf0 + c;
+            if (leaf >= n_leaves) break;
+            const bool active = enter(leaf);
+            const i64 p = leaf * LEAF + lane;
+            if (p < n) {
+                const u32 s = slots[p];
+                ids_dst[p] = ids_src[s];
+                const T* row = Psrc + (i64)s * d;
+                T* out = Pdst + p * d;
+#pragma unroll
+                for (int j = 0; j < MD; j++)
+                    if (j < d) {
+                        const T v = row[j];
+                        out[j] = v;
+                        if (active) {
+                            mn[j] = fminf(mn[j], (float)v);
+                            mx[j] = fmaxf(mx[j], (float)v);
+                        }
+                    }
+            }
+        }
+    }
+    flush();
+}
+
 // per node being split: widest axis, its lower bound and the quantisation scale of the sort key
 __global__ void __launch_bounds__(256) tree_node_split_info_kernel(const u32* __restrict__ nodeA, const u32* __restrict__ nodeB,
                                                                    const u32* __restrict__ bbox_lo, const u32* __restrict__ bbox_hi,
@@ -197,7 +334,7 @@ __global__ void __launch_bounds__(256) tree_make_keys_kernel(const T* __restrict
     if (nodeB[leaf] - a > 1) {
         // the coordinate along the node's widest axis, quantised to cbits within the node's box: the tree only
         // needs a balanced partition of reasonable quality, so ties inside one quantum may fall either side
-        const float x = (float)P[(i64)perm[p] * d + sdim[a]];
+        const float x = (float)P[(perm ? (i64)perm[p] : p) * d + sdim[a]];      // perm == nullptr: the rows are in position order
         const float top = (float)((1u << cbits) - 1u);
         float qf = (x - slo[a]) * sscale[a];
         qf = qf < 0.f ? 0.f : (qf > top ? top : qf);
@@ -255,7 +392,8 @@ static size_t tree_bottom_smem(int d) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __restrict__ P, u32* perm, i64 n, i64 n_leaves, int d, int cb) {
+__global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __restrict__ Pord, T* __restrict__ Pout, u32* perm, i64 n, i64 n_leaves,
+                                                                  int d, int cb) {
     extern __shared__ __align__(16) unsigned char bsm[];
     float* coords = (float*)bsm;                               // [d][BOT_POINTS]
     u32* ids = (u32*)(coords + (size_t)d * BOT_POINTS);        // [BOT_POINTS] original point ids
@@ -280,7 +418,7 @@ __global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __res
         u32 id = 0xffffffffu;
         if (s < np) {
             id = perm[p0 + s];
-            const T* row = P + (i64)id * d;
+            const T* row = Pord + (p0 + s) * d;        // the rows are in position order (tree_permute_bounds_kernel)
             for (int j = 0; j < d; j++) coords[(size_t)j * BOT_POINTS + s] = (float)row[j];
         }
         ids[s] = id;
@@ -385,10 +523,23 @@ __global__ void __launch_bounds__(BOT_THREADS) tree_bottom_kernel(const T* __res
         }
         __syncthreads();
     }
+    // the ids and -- for the tile builder, which then reads sequentially -- the rows, in final order
     for (int s = tid; s < np; s += BOT_THREADS) perm[p0 + s] = ids[order[s]];
+    if (sizeof(T) == 4) {
+        for (int e = tid; e < np * d; e += BOT_THREADS) {
+            const int s = e / d, j = e - s * d;
+            Pout[p0 * d + e] = (T)coords[(size_t)j * BOT_POINTS + order[s]];
+        }
+    } else {
+        // float64: shared memory holds rounded copies, so the exact rows are permuted through global memory
+        for (int e = tid; e < np * d; e += BOT_THREADS) {
+            const int s = e / d, j = e - s * d;
+            Pout[p0 * d + e] = Pord[(p0 + order[s]) * d + j];
+        }
+    }
 }
 
-// one warp per leaf: gather the leaf's points into its tile
+// one warp per leaf: the leaf's points (rows already in position order) into its tile
 template <typename T>
 __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restrict__ P, u32* perm, char* tiles,
                                                                T* box0, IndexHeader h) {
@@ -407,7 +558,7 @@ __global__ void __launch_bounds__(256) tree_build_tiles_kernel(const T* __restri
     const T inf = (T)INFINITY;
     int pb = lane >> 1, half = lane & 1;
     for (int j = 0; j < d; j++) {
-        T v = valid ? P[(i64)id * d + j] : inf;
+        T v = valid ? P[p * d + j] : inf;          // rows in position order
         coords[pb * h.pair_block + 2 * j + half] = v;
         T a = valid ? v : inf, b = valid ? v : -inf;
 #pragma unroll
@@ -454,6 +605,8 @@ struct BuildWs {
     int* sdim;
     float *slo, *sscale;
     u32 *nflag, *nrank;
+    u32 *iota, *slots;
+    void *rows0, *rows1;     // the point rows in the current order (ping-pong)
     void* cub_tmp;
     size_t cub_bytes;
 };
@@ -477,7 +630,6 @@ extern "C" int64_t al_index_positions(int64_t n) { return (n + LEAF - 1) / LEAF 
 extern "C" const uint32_t* al_index_perm(const void* index) { return (const uint32_t*)((const char*)index + 256); }
 
 extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
-    (void)dtype;
     i64 n_leaves = (n + LEAF - 1) / LEAF;
     ArenaSizer s;
     s.add<u32>(n);
@@ -492,6 +644,10 @@ extern "C" size_t al_index_build_workspace_bytes(int dtype, int64_t n, int d) {
     s.add<float>(n_leaves);
     s.add<u32>(n_leaves);
     s.add<u32>(n_leaves);
+    s.add<u32>(n);
+    s.add<u32>(n);
+    s.add<char>((size_t)n * d * (dtype == AL_F64 ? 8 : 4));
+    s.add<char>((size_t)n * d * (dtype == AL_F64 ? 8 : 4));
     s.add<char>(sort_temp_bytes(n));
     return s.off + 256;
 }
@@ -514,17 +670,24 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     w.sscale = ar.get<float>(n_leaves);
     w.nflag = ar.get<u32>(n_leaves);
     w.nrank = ar.get<u32>(n_leaves);
+    w.iota = ar.get<u32>(n);
+    w.slots = ar.get<u32>(n);
+    w.rows0 = ar.get<char>((size_t)n * d * sizeof(T));
+    w.rows1 = ar.get<char>((size_t)n * d * sizeof(T));
     w.cub_bytes = sort_temp_bytes(n);
     w.cub_tmp = ar.get<char>(w.cub_bytes);
     AL_REQUIRE(ar.ok, AL_ENOMEM, "al_index_build: workspace too small (%zu bytes given)", ws_bytes);
 
     char* base = (char*)index;
     u32* perm = (u32*)(base + h.perm_off);
-    u32* vals[2] = {perm, w.vals1};
-    u32* keys[2] = {w.keys0, w.keys1};
-    int cur = 0;
+    u32* ids[2] = {perm, w.vals1};       // point ids by position (ping-pong)
+    T* rows[2] = {(T*)w.rows0, (T*)w.rows1};
+    const T* Pcur = P;                   // point rows by position: the input itself while the order is the identity
+    int cur = 0, rc = 0;
 
     tree_init_kernel<<<al_grid(n, 256), 256, 0, st>>>(perm, w.nodeA, w.nodeB, n, n_leaves);
+    AL_CHECK_LAUNCH();
+    tree_init_kernel<<<al_grid(n, 256), 256, 0, st>>>(w.iota, w.nodeA, w.nodeB, n, n_leaves);
     AL_CHECK_LAUNCH();
 
     const int depth = tree_depth(n_leaves);
@@ -548,18 +711,23 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
     }
     int node_bits = 1;
     while (((i64)1 << node_bits) < n_leaves) node_bits++;
-    int cbits = 32 - node_bits;          // quantised-coordinate bits of the 32-bit sort key
-    if (cbits > 16) cbits = 16;
-    if (const char* e = getenv("AL_TREE_CBITS")) { int v = atoi(e); if (v >= 3 && v <= cbits) cbits = v; }   // development knob
-    AL_REQUIRE(cbits >= 5, AL_EINVAL, "al_index_build: too many leaves for 32-bit sort keys");
+    // quantised-coordinate bits of the 32-bit sort key: what the node bits of the round leave, up to a cap
+    int cbits_cap = 14;      // measured on C4 (build + search): 13: 70.44, 14: 70.25, 16: 70.34, 18: 70.48 ms
+    if (const char* e = getenv("AL_TREE_CBITS")) { int v = atoi(e); if (v >= 3 && v <= 24) cbits_cap = v; }   // development knob
+    AL_REQUIRE(32 - node_bits >= 5, AL_EINVAL, "al_index_build: too many leaves for 32-bit sort keys");
     int levels_done = 0;
+    const i64 leaves_per_block = (256 / 32) * BOUNDS_CHUNK;
+    const unsigned bounds_grid = (unsigned)((n_leaves + leaves_per_block - 1) / leaves_per_block);
     for (int r = 0; r < rounds; r++) {
-        AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
-        AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
-        const i64 leaves_per_block = (256 / 32) * BOUNDS_CHUNK;
-        tree_node_bounds_kernel<T><<<(unsigned)((n_leaves + leaves_per_block - 1) / leaves_per_block), 256, 0, st>>>(
-            P, vals[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, n, n_leaves, d);
-        AL_CHECK_LAUNCH();
+        const int rank_bits = levels_done < node_bits ? levels_done : node_bits;      // at most 2^levels_done nodes exist
+        const int cbits = 32 - rank_bits < cbits_cap ? 32 - rank_bits : cbits_cap;
+        if (r == 0) {
+            // (later rounds: the boxes were accumulated by the previous round's permutation pass)
+            AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
+            AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
+            tree_node_bounds_kernel<T><<<bounds_grid, 256, 0, st>>>(P, ids[cur], w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, n, n_leaves, d);
+            AL_CHECK_LAUNCH();
+        }
         tree_node_split_info_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, w.bbox_lo, w.bbox_hi, w.sdim,
                                                                                        w.slo, w.sscale, n_leaves, d, cbits);
         AL_CHECK_LAUNCH();
@@ -569,29 +737,53 @@ static int index_build_impl(const T* P, const IndexHeader& h, void* index, void*
         size_t sb = w.cub_bytes;
         AL_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, sb, w.nflag, w.nrank, n_leaves, st));
         tree_make_keys_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            P, vals[cur], w.nodeA, w.nodeB, w.sdim, w.slo, w.sscale, w.nrank, keys[cur], n, d, cbits);
+            Pcur, nullptr, w.nodeA, w.nodeB, w.sdim, w.slo, w.sscale, w.nrank, w.keys0, n, d, cbits);
         AL_CHECK_LAUNCH();
         size_t tb = w.cub_bytes;
-        int rank_bits = levels_done < node_bits ? levels_done : node_bits;      // at most 2^levels_done nodes exist
-        AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, 0,
-                                                cbits + rank_bits, st));
+        // the sort carries positions (slots), not ids: the rows and ids follow in the permutation pass below
+        AL_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys0, w.keys1, w.iota, w.slots, n, 0, cbits + rank_bits, st));
         levels_done += sched[r];
-        cur ^= 1;
         tree_split_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(w.nodeA, w.nodeB, n_leaves, sched[r]);
         AL_CHECK_LAUNCH();
+        const int want_bounds = r + 1 < rounds ? 1 : 0;
+        if (want_bounds) {
+            AL_CUDA(cudaMemsetAsync(w.bbox_lo, 0xff, sizeof(u32) * n_leaves * d, st));
+            AL_CUDA(cudaMemsetAsync(w.bbox_hi, 0x00, sizeof(u32) * n_leaves * d, st));
+        }
+        // rows of a whole number of 8-byte units (and an 8-byte aligned input) take the vector path
+        const bool v8 = ((size_t)d * sizeof(T)) % 8 == 0 && ((uintptr_t)Pcur & 7u) == 0;
+#define AL_PERMUTE(V, M, F)                                                                                                               \
+    tree_permute_bounds_kernel<T, V, M, F><<<bounds_grid, 256, 0, st>>>(Pcur, ids[cur], w.slots, rows[rc], ids[cur ^ 1], w.nodeA, w.nodeB, \
+                                                                        w.bbox_lo, w.bbox_hi, n, n_leaves, d, want_bounds)
+        // (two leaves in flight; one or four measured the same: 5.92 / 5.88 / 5.89 ms for the whole build at C4)
+        bool launched = false;
+        if (v8 && d <= 8) { AL_PERMUTE(true, 8, 2); launched = true; }
+        if constexpr (sizeof(T) == 4) {      // (float64 rows of more than 8 coordinates would not fit the staging buffer)
+            if (!launched && v8) { AL_PERMUTE(true, MAXD, 2); launched = true; }
+        }
+        if (!launched) {
+            if (d <= 8) AL_PERMUTE(false, 8, 1);
+            else AL_PERMUTE(false, MAXD, 1);
+        }
+#undef AL_PERMUTE
+        AL_CHECK_LAUNCH();
+        Pcur = rows[rc];
+        rc ^= 1;
+        cur ^= 1;
     }
-    if (vals[cur] != perm) AL_CUDA(cudaMemcpyAsync(perm, vals[cur], sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+    if (ids[cur] != perm) AL_CUDA(cudaMemcpyAsync(perm, ids[cur], sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
     if (use_bottom && depth > 0) {
         const size_t smem = tree_bottom_smem(d);
         AL_CUDA(cudaFuncSetAttribute(tree_bottom_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int cb = 10;      // coordinate bits of the in-block sort key: children overlap by at most 1/1024 of the node extent
         if (const char* e = getenv("AL_TREE_BOT_CBITS")) { int v = atoi(e); if (v >= 5 && v <= 16) cb = v; }   // development knob
-        tree_bottom_kernel<T><<<(unsigned)((n_leaves + BOT_LEAVES - 1) / BOT_LEAVES), BOT_THREADS, smem, st>>>(P, perm, n, n_leaves, d, cb);
+        tree_bottom_kernel<T><<<(unsigned)((n_leaves + BOT_LEAVES - 1) / BOT_LEAVES), BOT_THREADS, smem, st>>>(Pcur, rows[rc], perm, n, n_leaves, d, cb);
         AL_CHECK_LAUNCH();
+        Pcur = rows[rc];
     }
 
     T* box0 = (T*)(base + h.box_off[0]);
-    tree_build_tiles_kernel<T><<<(unsigned)((n_leaves * 32 + 255) / 256), 256, 0, st>>>(P, perm, base + h.tiles_off, box0, h);
+    tree_build_tiles_kernel<T><<<(unsigned)((n_leaves * 32 + 255) / 256), 256, 0, st>>>(Pcur, perm, base + h.tiles_off, box0, h);
     AL_CHECK_LAUNCH();
     for (int l = 1; l <= h.n_levels; l++) {
         const T* cbox = (const T*)(base + h.box_off[l - 1]);
