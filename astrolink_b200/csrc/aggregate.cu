@@ -5,6 +5,7 @@
 
 #include <iterator>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/discard_iterator.h>
 
 #include "aggregate_impl.h"
 #include "common.cuh"
@@ -97,6 +98,27 @@ struct CudaExec {
         void* tmp = ar.get<char>(tb);
         if (!ar.ok) { ar.reset(mk); return; }
         note(cub::DeviceSelect::If(tmp, tb, in, out, count_dev, n, op, st));
+        launches++;
+        ar.reset(mk);
+    }
+    // two selections in ONE pass over [0, n): for every i with pred1(i), in order, emit1(i, rank among those); for every other
+    // i with pred2(i), in order, emit2(i, rank among those); the counts go to count_dev[0] and count_dev[1]
+    // (cub::DevicePartition::If, three-way: both selected parts keep their relative order; the rest is discarded)
+    template <class Tag, class Pred1, class Emit1, class Pred2, class Emit2>
+    void select2(i64 n, Pred1 pred1, Emit1 emit1, Pred2 pred2, Emit2 emit2, u32* count_dev, AggArena& ar) {
+        if (n <= 0) { note(cudaMemsetAsync(count_dev, 0, 8, st)); return; }
+        const size_t mk = ar.mark();
+        thrust::counting_iterator<u32> in(0u);
+        AggEmitIterator<Emit1> out1{emit1, 0};
+        AggEmitIterator<Emit2> out2{emit2, 0};
+        thrust::discard_iterator<> rest;
+        AggPredOp<Pred1> op1{pred1};
+        AggPredOp<Pred2> op2{pred2};
+        size_t tb = 0;
+        note(cub::DevicePartition::If(nullptr, tb, in, out1, out2, rest, count_dev, n, op1, op2, st));
+        void* tmp = ar.get<char>(tb);
+        if (!ar.ok) { ar.reset(mk); return; }
+        note(cub::DevicePartition::If(tmp, tb, in, out1, out2, rest, count_dev, n, op1, op2, st));
         launches++;
         ar.reset(mk);
     }

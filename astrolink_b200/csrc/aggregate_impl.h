@@ -208,11 +208,14 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
             const uint2_agg* e_ = ep;
             const u32* r_ = er;
             const i64 M_ = M;
-            // Two stable single-pass selections over the edge list (no flag arrays, no prefix sums of them):
+            // Two stable selections in ONE pass over the edge list (no flag arrays, no prefix sums of them):
             // (1) the picked edges, in list (= rank) order, become this level's records; the vertices that picked an edge
             //     learn where it went (nodefirst);
+            // (2) the survivors -- not picked, endpoints in different new components -- relabelled, form the next level's list.
             x.fill_u32(nodefirst, NONE, N);
-            x.template select<TagRecord>(m, AGG_LAMBDA(i64 i) { return ((pickbits[i >> 5] >> (i & 31)) & 1u) != 0u; }, AGG_LAMBDA(i64 i, i64 pos) {
+            uint2_agg* eo = ep_next;
+            u32* ro = er_next;
+            x.template select2<TagRecord>(m, AGG_LAMBDA(i64 i) { return ((pickbits[i >> 5] >> (i & 31)) & 1u) != 0u; }, AGG_LAMBDA(i64 i, i64 pos) {
                 const uint2_agg e = e_[i];
                 const i64 c = M_ + pos;
                 pk_rank[c] = r_ ? r_[i] : (u32)i;
@@ -222,12 +225,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 pk_picker[c] = (fx && fy) ? NONE : (fx ? e.x : e.y);
                 if (fx) nodefirst[e.x] = (u32)c;
                 if (fy) nodefirst[e.y] = (u32)c;
-            }, tot + 1, ar);
-            // (2) the survivors -- not picked, endpoints in different new components -- relabelled, form the next level's list.
-            uint2_agg* eo = ep_next;
-            u32* ro = er_next;
-            x.template select<TagCompact>(m, AGG_LAMBDA(i64 i) {
-                if ((pickbits[i >> 5] >> (i & 31)) & 1u) return false;
+            }, AGG_LAMBDA(i64 i) {
                 const uint2_agg e = e_[i];
                 return label[e.x] != label[e.y];
             }, AGG_LAMBDA(i64 i, i64 pos) {
@@ -237,7 +235,7 @@ int run(X& x, AggArena& ar, const T* logrho, const u32* sorted_pairs, i64 n, i64
                 ne.y = label[e.y];
                 eo[pos] = ne;
                 ro[pos] = r_ ? r_[i] : (u32)i;
-            }, tot + 2, ar);
+            }, tot + 1, ar);
             // the round's only host read: components, picked edges and surviving edges
             u32 h3[3];
             x.read_u32s(tot, h3, 3);

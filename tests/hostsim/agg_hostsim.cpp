@@ -49,6 +49,17 @@ struct HostExec {
         for (i64 i = 0; i < n; i++) if (keep[(size_t)i]) emit(i, pos++);
         count[0] = (u32)pos;
     }
+    template <class Tag, class Pred1, class Emit1, class Pred2, class Emit2>
+    void select2(i64 n, Pred1 pred1, Emit1 emit1, Pred2 pred2, Emit2 emit2, u32* count, AggArena&) {
+        // as select: all predicates first, then the emits (first part, then second part; on the GPU they interleave)
+        std::vector<char> part((size_t)(n > 0 ? n : 0));
+        launch<Tag>(n, [&](i64 i) { part[(size_t)i] = pred1(i) ? 1 : (pred2(i) ? 2 : 0); });
+        i64 p1 = 0, p2 = 0;
+        for (i64 i = 0; i < n; i++) if (part[(size_t)i] == 1) emit1(i, p1++);
+        for (i64 i = 0; i < n; i++) if (part[(size_t)i] == 2) emit2(i, p2++);
+        count[0] = (u32)p1;
+        count[1] = (u32)p2;
+    }
     void fill_u32(u32* p, u32 v, i64 n) { for (i64 i = 0; i < n; i++) p[i] = v; }
     void read_u32s(const u32* p, u32* host, int count) { for (int i = 0; i < count; i++) host[i] = p[i]; }
     void exclusive_sum_u32(const u32* in, u32* out, i64 n, AggArena&, u32* total) {
