@@ -54,7 +54,42 @@ def main():
     hdr, units = rows[0], rows[1]
     ix = {k: i for i, k in enumerate(hdr)}
     print(f"# {os.path.basename(rep)}: {len(rows) - 2} captured launch(es); HBM peak {peak} GB/s (MEASURED_PEAKS.json)")
-    for r in rows[2:]:
+    body = rows[2:]
+    if "--by-name" in sys.argv:
+        # one line per kernel (template arguments shortened): launches, total time, DRAM bytes, GB/s; then the full block of the
+        # longest launch of each of the top kernels only
+        def num(r, key):
+            if key not in ix or r[ix[key]] == "":
+                return 0.0
+            return float(r[ix[key]].replace(",", "")) * UNIT.get(units[ix[key]], 1.0)
+        import re
+        def short(name):
+            m = re.search(r"agg::(Tag\w+)", name)
+            if m:
+                return ("agg_kernel_if<" if "agg_kernel_if" in name else "agg_kernel<") + m.group(1) + ">"
+            return name.split("(")[0][:60]
+        agg = collections.OrderedDict()
+        for r in body:
+            k = short(r[ix["Kernel Name"]])
+            a = agg.setdefault(k, [0, 0.0, 0.0, 0.0, None, 0.0])
+            t = num(r, "gpu__time_duration.sum")
+            a[0] += 1
+            a[1] += t
+            a[2] += num(r, "dram__bytes_read.sum")
+            a[3] += num(r, "dram__bytes_write.sum")
+            if t > a[5]:
+                a[4], a[5] = r, t
+        tot = sum(a[1] for a in agg.values())
+        print(f"# by kernel (total {tot * 1e3:.3f} ms under ncu: cold caches, serialised)")
+        print(f"# {'kernel':44s} {'launches':>8s} {'ms':>9s} {'share':>6s} {'DRAM MB':>9s} {'GB/s':>8s} {'of peak':>7s}")
+        top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        for k, a in top:
+            gbs = (a[2] + a[3]) / a[1] / 1e9 if a[1] > 0 else 0.0
+            print(f"  {k:44s} {a[0]:8d} {a[1] * 1e3:9.3f} {a[1] / tot:6.3f} {(a[2] + a[3]) / 1e6:9.1f} {gbs:8.1f} {gbs / peak:7.3f}")
+        body = [a[4] for k, a in top[:6]]
+        print()
+        print("# full metrics of the longest launch of each of the six kernels with the most time:")
+    for r in body:
         print()
         print(r[ix["Kernel Name"]][:150])
 
